@@ -1,0 +1,800 @@
+// api.cu — the C-ABI of include/mnv1.h: context, buffers, filters, the four kernel entry
+// points with kernel.cl's argument order, and the whole-network executor (activation arena +
+// CUDA graph) that replaces the 29 copy-pasted layer blocks of MobileNet.c:207-2763.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace mnv1 {
+int load_weight_file(const char* path, std::vector<float>* weights, std::vector<float>* scale,
+                     std::vector<float>* shift, std::string* err);
+int save_weight_file_bin(const char* path, const float* weights, const float* scale, const float* shift,
+                         std::string* err);
+int read_ppm(const char* path, uint8_t* out, int height, int width, std::string* err);
+}  // namespace mnv1
+
+static thread_local std::string g_last_error;
+
+struct LayerDef { int kind, cin, cout, hin, hout, stride; long w_off, w_cnt, c_off; };
+
+static const LayerDef* layer_defs() {
+  static LayerDef L[MNV1_NUM_LAYERS];
+  static bool init = false;
+  if (!init) {
+    // MobileNet.c schedule; L26 is stride 1 (App. B note)
+    const int dw_c[13] = {32, 64, 128, 128, 256, 256, 512, 512, 512, 512, 512, 512, 1024};
+    const int dw_s[13] = {1, 2, 1, 2, 1, 2, 1, 1, 1, 1, 1, 2, 1};
+    const int pw_o[13] = {64, 128, 128, 256, 256, 512, 512, 512, 512, 512, 512, 1024, 1024};
+    long w = 0, c = 0;
+    int h = 112, k = 0;
+    L[k++] = {MNV1_CONVOLUTE, 3, 32, 224, 112, 2, 0, 864, 0};
+    w = 864; c = 32;
+    for (int b = 0; b < 13; ++b) {
+      const int ho = h / dw_s[b];
+      L[k++] = {MNV1_DEPTHWISE, dw_c[b], dw_c[b], h, ho, dw_s[b], w, dw_c[b] * 9L, c};
+      w += dw_c[b] * 9L; c += dw_c[b]; h = ho;
+      L[k++] = {MNV1_POINTWISE, dw_c[b], pw_o[b], h, h, 1, w, (long)dw_c[b] * pw_o[b], c};
+      w += (long)dw_c[b] * pw_o[b]; c += pw_o[b];
+    }
+    L[k++] = {MNV1_POOL, 1024, 1024, 7, 1, 1, w, 0, c};
+    L[k++] = {MNV1_FC, 1024, 1000, 1, 1, 1, w, 1024000L, c};
+    init = true;
+  }
+  return L;
+}
+
+struct GraphKey {
+  const void* img; int n; void* logits; void* top1; void* prob;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(img, n, logits, top1, prob) < std::tie(o.img, o.n, o.logits, o.top1, o.prob);
+  }
+};
+
+struct mnv1_ctx {
+  int device = 0;
+  mnv1_dtype dtype = MNV1_F32;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  mnv1_pad pad = MNV1_PAD_REF;
+  float in_scale = 1.f, in_bias = 0.f;
+  int num_sms = 148;
+  bool timing = true;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
+  long launches = 0;
+  std::string err;
+  const char* last_kernel = "";
+  // whole-network state
+  mnv1_filter* net[MNV1_NUM_LAYERS] = {};
+  bool have_weights = false;
+  int plan_batch = 0;
+  void* act[2] = {nullptr, nullptr};
+  uint8_t* d_images = nullptr;
+  float* d_pooled = nullptr;
+  float* d_logits = nullptr;
+  int* d_top1 = nullptr;
+  float* d_prob = nullptr;
+  uint8_t* h_images = nullptr;  // pinned staging
+  float* h_logits = nullptr;
+  int* h_top1 = nullptr;
+  float* h_prob = nullptr;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  bool use_graph = true;
+};
+
+static int fail(mnv1_ctx* ctx, int code, const std::string& msg) {
+  g_last_error = msg;
+  if (ctx) ctx->err = msg;
+  return code;
+}
+static int fail_cuda(mnv1_ctx* ctx, cudaError_t e, const char* what) {
+  std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+  if (ctx && !ctx->err.empty() && e == cudaErrorInvalidValue) m += " (" + ctx->err + ")";
+  return fail(ctx, MNV1_ECUDA, m);
+}
+#define CK(ctx, call)                                                  \
+  do {                                                                 \
+    cudaError_t e_ = (call);                                           \
+    if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);           \
+  } while (0)
+
+static size_t elem_size(mnv1_dtype dt) { return dt == MNV1_BF16 ? 2 : 4; }
+static int pad_lo_for(const mnv1_ctx* ctx, int stride) {
+  return (stride == 2 && ctx->pad == MNV1_PAD_TFSAME) ? 0 : 1;
+}
+
+struct TimedLaunch {  // brackets one per-layer launch with the event pair (MobileNet.c:303-305)
+  mnv1_ctx* c;
+  explicit TimedLaunch(mnv1_ctx* ctx) : c(ctx) {
+    if (c->timing) cudaEventRecord(c->ev0, c->stream);
+  }
+  ~TimedLaunch() {
+    if (c->timing) { cudaEventRecord(c->ev1, c->stream); c->ev_valid = true; }
+  }
+};
+
+extern "C" {
+
+const char* mnv1_version(void) { return "mnv1-b200 0.1 (sm_100a)"; }
+
+const char* mnv1_last_error(const mnv1_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int mnv1_ctx_create(int device, mnv1_dtype dtype, mnv1_ctx** out) {
+  if (!out || (dtype != MNV1_F32 && dtype != MNV1_BF16)) return fail(nullptr, MNV1_EINVAL, "bad ctx_create args");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(nullptr, MNV1_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                         " (this library has no CPU fallback)");
+  if (device < 0 || device >= count) return fail(nullptr, MNV1_EINVAL, "device index out of range");
+  CK(nullptr, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(nullptr, cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(nullptr, MNV1_EUNSUPPORTED, std::string("device ") + prop.name +
+                                                " is not sm_100 (kernels are built for sm_100a only)");
+  std::unique_ptr<mnv1_ctx> ctx(new mnv1_ctx);
+  ctx->device = device;
+  ctx->dtype = dtype;
+  ctx->num_sms = prop.multiProcessorCount;
+  CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(nullptr, cudaEventCreate(&ctx->ev0));
+  CK(nullptr, cudaEventCreate(&ctx->ev1));
+  *out = ctx.release();
+  return MNV1_OK;
+}
+
+static void free_plan(mnv1_ctx* ctx) {
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  ctx->graphs.clear();
+  for (int i = 0; i < 2; ++i) { cudaFree(ctx->act[i]); ctx->act[i] = nullptr; }
+  cudaFree(ctx->d_images); cudaFree(ctx->d_pooled); cudaFree(ctx->d_logits); cudaFree(ctx->d_top1);
+  cudaFree(ctx->d_prob);
+  cudaFreeHost(ctx->h_images); cudaFreeHost(ctx->h_logits); cudaFreeHost(ctx->h_top1); cudaFreeHost(ctx->h_prob);
+  ctx->d_images = nullptr; ctx->d_pooled = nullptr; ctx->d_logits = nullptr; ctx->d_top1 = nullptr;
+  ctx->d_prob = nullptr; ctx->h_images = nullptr; ctx->h_logits = nullptr; ctx->h_top1 = nullptr;
+  ctx->h_prob = nullptr;
+  ctx->plan_batch = 0;
+}
+
+int mnv1_filter_destroy(mnv1_ctx* ctx, mnv1_filter* f);
+
+int mnv1_ctx_destroy(mnv1_ctx* ctx) {
+  if (!ctx) return MNV1_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_plan(ctx);
+  for (auto& f : ctx->net) { if (f) mnv1_filter_destroy(ctx, f); f = nullptr; }
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return MNV1_OK;
+}
+
+int mnv1_ctx_set_stream(mnv1_ctx* ctx, void* s) {
+  if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
+  if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  ctx->stream = (cudaStream_t)s;
+  ctx->own_stream = false;
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  ctx->graphs.clear();
+  return MNV1_OK;
+}
+int mnv1_ctx_set_pad_mode(mnv1_ctx* ctx, mnv1_pad pad) {
+  if (!ctx || (pad != MNV1_PAD_REF && pad != MNV1_PAD_TFSAME)) return fail(ctx, MNV1_EINVAL, "bad pad mode");
+  ctx->pad = pad;
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  ctx->graphs.clear();
+  return MNV1_OK;
+}
+int mnv1_ctx_set_input_transform(mnv1_ctx* ctx, float scale, float bias) {
+  if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
+  ctx->in_scale = scale; ctx->in_bias = bias;
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  ctx->graphs.clear();
+  return MNV1_OK;
+}
+int mnv1_ctx_enable_timing(mnv1_ctx* ctx, int on) {
+  if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
+  ctx->timing = on != 0;
+  return MNV1_OK;
+}
+int mnv1_sync(mnv1_ctx* ctx) {
+  if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return MNV1_OK;
+}
+int mnv1_last_kernel_ms(mnv1_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return fail(ctx, MNV1_EINVAL, "null arg");
+  if (!ctx->timing || !ctx->ev_valid) return fail(ctx, MNV1_ESTATE, "no timed launch yet");
+  CK(ctx, cudaEventSynchronize(ctx->ev1));
+  CK(ctx, cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return MNV1_OK;
+}
+long mnv1_launch_count(const mnv1_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* mnv1_last_kernel_name(const mnv1_ctx* ctx) { return ctx ? ctx->last_kernel : ""; }
+
+// ---------------------------------------------------------------- buffers
+int mnv1_malloc(mnv1_ctx* ctx, int n, int c, int h, int w, mnv1_buf** out) {
+  if (!ctx || !out || n < 0 || c <= 0 || h <= 0 || w <= 0) return fail(ctx, MNV1_EINVAL, "bad malloc shape");
+  std::unique_ptr<mnv1_buf> b(new mnv1_buf);
+  b->n = n; b->c = c; b->h = h; b->w = w;
+  b->bytes = (size_t)n * c * h * w * elem_size(ctx->dtype);
+  if (b->bytes) {
+    cudaError_t e = cudaMalloc(&b->d, b->bytes);
+    if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  *out = b.release();
+  return MNV1_OK;
+}
+int mnv1_malloc_u8(mnv1_ctx* ctx, size_t bytes, mnv1_buf** out) {
+  if (!ctx || !out) return fail(ctx, MNV1_EINVAL, "null arg");
+  std::unique_ptr<mnv1_buf> b(new mnv1_buf);
+  b->bytes = bytes; b->is_u8 = true;
+  if (bytes) {
+    cudaError_t e = cudaMalloc(&b->d, bytes);
+    if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  *out = b.release();
+  return MNV1_OK;
+}
+int mnv1_free(mnv1_ctx* ctx, mnv1_buf* b) {
+  if (!b) return MNV1_OK;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (b->owned && b->d) cudaFree(b->d);
+  delete b;
+  return MNV1_OK;
+}
+void* mnv1_buf_device_ptr(mnv1_buf* b) { return b ? b->d : nullptr; }
+
+int mnv1_upload_u8(mnv1_ctx* ctx, mnv1_buf* b, const uint8_t* host, size_t bytes) {
+  if (!ctx || !b || !b->is_u8 || bytes > b->bytes || (!host && bytes)) return fail(ctx, MNV1_EINVAL, "bad upload_u8");
+  if (bytes) CK(ctx, cudaMemcpyAsync(b->d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));  // CL_TRUE blocking write, MobileNet.c:350
+  return MNV1_OK;
+}
+int mnv1_upload_planar(mnv1_ctx* ctx, mnv1_buf* b, const float* host) {
+  if (!ctx || !b || b->is_u8 || (!host && b->bytes)) return fail(ctx, MNV1_EINVAL, "bad upload_planar");
+  if (!b->bytes) return MNV1_OK;
+  const size_t elems = (size_t)b->n * b->c * b->h * b->w;
+  float* stage = nullptr;
+  cudaError_t e = cudaMalloc(&stage, elems * 4);
+  if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "staging cudaMalloc failed");
+  e = cudaMemcpyAsync(stage, host, elems * 4, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = mnv1::launch_nchw_to_nhwc(ctx->dtype, b->d, stage, b->n, b->c, b->h, b->w, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(stage);
+  ctx->launches++;
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "upload_planar");
+  return MNV1_OK;
+}
+int mnv1_download_planar(mnv1_ctx* ctx, mnv1_buf* b, float* host) {
+  if (!ctx || !b || b->is_u8 || (!host && b->bytes)) return fail(ctx, MNV1_EINVAL, "bad download_planar");
+  if (!b->bytes) return MNV1_OK;
+  const size_t elems = (size_t)b->n * b->c * b->h * b->w;
+  float* stage = nullptr;
+  cudaError_t e = cudaMalloc(&stage, elems * 4);
+  if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "staging cudaMalloc failed");
+  e = mnv1::launch_nhwc_to_nchw(ctx->dtype, stage, b->d, b->n, b->c, b->h, b->w, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host, stage, elems * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(stage);
+  ctx->launches++;
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "download_planar");
+  return MNV1_OK;
+}
+
+// ---------------------------------------------------------------- filters
+static int upload_vec(mnv1_ctx* ctx, const std::vector<float>& v, float** d) {
+  cudaError_t e = cudaMalloc(d, v.size() * 4);
+  if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "cudaMalloc(filter) failed");
+  CK(ctx, cudaMemcpy(*d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  return MNV1_OK;
+}
+static uint16_t f32_to_bf16_rne(float x) {
+  uint32_t u; memcpy(&u, &x, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, int cout, const float* scale,
+                       const float* shift, mnv1_act act, mnv1_filter** out) {
+  if (!ctx || !w || !out || cin <= 0 || cout <= 0) return fail(ctx, MNV1_EINVAL, "bad filter_create args");
+  std::unique_ptr<mnv1_filter> f(new mnv1_filter);
+  f->kind = kind; f->cin = cin; f->cout = cout; f->act = act;
+  std::vector<float> dev;
+  int rc = MNV1_OK;
+  switch (kind) {
+    case MNV1_CONVOLUTE: {  // [O][3(R,G,B)][3][3] (kernel.cl:15-51 findex order) -> [27][O]
+      if (cin != 3) return fail(ctx, MNV1_EINVAL, "convolute filter needs cin == 3");
+      dev.resize((size_t)27 * cout);
+      for (int o = 0; o < cout; ++o)
+        for (int t = 0; t < 27; ++t) dev[(size_t)t * cout + o] = w[(size_t)o * 27 + t];
+      break;
+    }
+    case MNV1_DEPTHWISE: {  // [C][3][3] (kernel.cl:77) -> [9][C]
+      if (cin != cout) return fail(ctx, MNV1_EINVAL, "depthwise filter needs cin == cout");
+      dev.resize((size_t)9 * cout);
+      for (int c = 0; c < cout; ++c)
+        for (int t = 0; t < 9; ++t) dev[(size_t)t * cout + c] = w[(size_t)c * 9 + t];
+      break;
+    }
+    case MNV1_POINTWISE:
+    case MNV1_FC:           // [Cout][Cin] (kernel.cl:106) kept as is: it is the K-major B operand
+      dev.assign(w, w + (size_t)cin * cout);
+      break;
+    default:
+      return fail(ctx, MNV1_EINVAL, "filter kind has no weights");
+  }
+  if ((rc = upload_vec(ctx, dev, &f->w_f32)) != MNV1_OK) return rc;
+  if (scale) { std::vector<float> s(scale, scale + cout); if ((rc = upload_vec(ctx, s, &f->scale)) != MNV1_OK) return rc; }
+  if (shift) { std::vector<float> s(shift, shift + cout); if ((rc = upload_vec(ctx, s, &f->shift)) != MNV1_OK) return rc; }
+  if (ctx->dtype == MNV1_BF16 && (kind == MNV1_POINTWISE || kind == MNV1_FC)) {
+    std::vector<uint16_t> h((size_t)cin * cout);
+    for (size_t i = 0; i < h.size(); ++i) h[i] = f32_to_bf16_rne(w[i]);
+    cudaError_t e = cudaMalloc(&f->w_bf16, h.size() * 2);
+    if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "cudaMalloc(filter bf16) failed");
+    CK(ctx, cudaMemcpy(f->w_bf16, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+    if (kind == MNV1_POINTWISE && cout % 32 == 0 && cin % 8 == 0 && cout <= 1024) {
+      std::string err;
+      cudaError_t te = mnv1::make_weight_tmap(f.get(), &err);
+      if (te != cudaSuccess) return fail(ctx, MNV1_ECUDA, "TMA descriptor for pointwise filter: " + err);
+    }
+  }
+  *out = f.release();
+  return MNV1_OK;
+}
+int mnv1_filter_destroy(mnv1_ctx* ctx, mnv1_filter* f) {
+  if (!f) return MNV1_OK;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  cudaFree(f->w_f32); cudaFree(f->w_bf16); cudaFree(f->scale); cudaFree(f->shift);
+  delete f;
+  return MNV1_OK;
+}
+
+// ---------------------------------------------------------------- raw launches (device pointers)
+static cudaError_t run_stem(mnv1_ctx* ctx, void* out, const uint8_t* r, const uint8_t* g, const uint8_t* b,
+                            int pix_stride, long img_stride, const mnv1_filter* f, int n, int rows, int cols,
+                            int stride) {
+  mnv1::StemArgs a{r, g, b, pix_stride, img_stride, n, rows, cols, stride, f->cout, pad_lo_for(ctx, stride),
+                   ctx->in_scale, ctx->in_bias};
+  ctx->launches++; ctx->last_kernel = "stem_kernel";
+  return mnv1::launch_stem(ctx->dtype, out, a, f->w_f32, Epilogue{f->scale, f->shift, (int)f->act}, ctx->stream);
+}
+static cudaError_t run_depthwise(mnv1_ctx* ctx, void* out, const void* in, const mnv1_filter* f, int n, int rows,
+                                 int cols, int stride) {
+  ctx->launches++; ctx->last_kernel = "depthwise_kernel";
+  return mnv1::launch_depthwise(ctx->dtype, out, in, f->w_f32, n, rows, cols, stride, f->cout,
+                                pad_lo_for(ctx, stride), Epilogue{f->scale, f->shift, (int)f->act}, ctx->stream);
+}
+static cudaError_t run_pointwise(mnv1_ctx* ctx, void* out, const void* in, const mnv1_filter* f, long m,
+                                 bool force_simt) {
+  ctx->launches++;
+  if (ctx->dtype == MNV1_BF16 && f->has_tmap && !force_simt) {
+    ctx->last_kernel = "pointwise_tc_kernel";
+    ctx->err.clear();
+    return mnv1::launch_pointwise_tc((bf16*)out, (const bf16*)in, f, m, f->cin, f->cout, ctx->num_sms,
+                                     ctx->stream, &ctx->err);
+  }
+  ctx->last_kernel = "pointwise_simt_kernel";
+  return mnv1::launch_pointwise_simt(ctx->dtype, out, in, f->w_f32, f->w_bf16, m, f->cin, f->cout,
+                                     Epilogue{f->scale, f->shift, (int)f->act}, false, ctx->stream);
+}
+
+// ---------------------------------------------------------------- the four kernels
+static int check_fmap(mnv1_ctx* ctx, const mnv1_buf* b, int c, int h, int w, const char* what) {
+  if (!b || b->is_u8 || b->c != c || b->h != h || b->w != w)
+    return fail(ctx, MNV1_EINVAL, std::string(what) + ": buffer shape does not match the kernel arguments");
+  return MNV1_OK;
+}
+
+static int convolute_common(mnv1_ctx* ctx, mnv1_buf* out, const uint8_t* r, const uint8_t* g, const uint8_t* b,
+                            int pix_stride, size_t avail_bytes, const mnv1_filter* f, int rows, int cols,
+                            int filtersize, int stride, int op_size) {
+  if (!ctx || !out || !f) return fail(ctx, MNV1_EINVAL, "convolute: null argument");
+  if (f->kind != MNV1_CONVOLUTE || f->cout != op_size) return fail(ctx, MNV1_EINVAL, "convolute: filter mismatch");
+  if (filtersize != 3) return fail(ctx, MNV1_EUNSUPPORTED, "convolute: only 3x3 (K = 3, MobileNet.c:15)");
+  if (op_size != 32) return fail(ctx, MNV1_EUNSUPPORTED, "convolute: op_size must be 32 (FILTER_SIZE_L1)");
+  if ((stride != 1 && stride != 2) || rows % stride || cols % stride)
+    return fail(ctx, MNV1_EUNSUPPORTED, "convolute: stride must be 1 or 2 and divide rows/cols");
+  int rc = check_fmap(ctx, out, op_size, rows / stride, cols / stride, "convolute(out)");
+  if (rc) return rc;
+  const size_t plane = (size_t)rows * cols * pix_stride;
+  if (avail_bytes < plane * out->n) return fail(ctx, MNV1_EINVAL, "convolute: image buffer too small for the batch");
+  TimedLaunch tl(ctx);
+  CK(ctx, run_stem(ctx, out->d, r, g, b, pix_stride, (long)plane, f, out->n, rows, cols, stride));
+  return MNV1_OK;
+}
+
+int mnv1_convolute(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in_r, const mnv1_buf* in_g, const mnv1_buf* in_b,
+                   const mnv1_filter* f, int rows, int cols, int filtersize, int stride, int op_size) {
+  if (!in_r || !in_g || !in_b || !in_r->is_u8 || !in_g->is_u8 || !in_b->is_u8)
+    return fail(ctx, MNV1_EINVAL, "convolute: r/g/b must be u8 buffers");
+  size_t avail = in_r->bytes < in_g->bytes ? in_r->bytes : in_g->bytes;
+  if (in_b->bytes < avail) avail = in_b->bytes;
+  return convolute_common(ctx, out, (const uint8_t*)in_r->d, (const uint8_t*)in_g->d, (const uint8_t*)in_b->d, 1,
+                          avail, f, rows, cols, filtersize, stride, op_size);
+}
+int mnv1_convolute_rgb(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in_rgb, const mnv1_filter* f, int rows,
+                       int cols, int filtersize, int stride, int op_size) {
+  if (!in_rgb || !in_rgb->is_u8) return fail(ctx, MNV1_EINVAL, "convolute_rgb: image must be a u8 buffer");
+  const uint8_t* p = (const uint8_t*)in_rgb->d;
+  return convolute_common(ctx, out, p, p + 1, p + 2, 3, in_rgb->bytes, f, rows, cols, filtersize, stride, op_size);
+}
+
+int mnv1_depthwise(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* f, int rows, int cols,
+                   int filtersize, int stride, int op_size) {
+  if (!ctx || !out || !in || !f) return fail(ctx, MNV1_EINVAL, "depthwise: null argument");
+  if (f->kind != MNV1_DEPTHWISE || f->cout != op_size) return fail(ctx, MNV1_EINVAL, "depthwise: filter mismatch");
+  if (filtersize != 3) return fail(ctx, MNV1_EUNSUPPORTED, "depthwise: only 3x3 (K = 3, MobileNet.c:15)");
+  if ((stride != 1 && stride != 2) || rows % stride || cols % stride)
+    return fail(ctx, MNV1_EUNSUPPORTED, "depthwise: stride must be 1 or 2 and divide rows/cols");
+  const int vec = ctx->dtype == MNV1_BF16 ? 8 : 4;
+  if (op_size % vec) return fail(ctx, MNV1_EUNSUPPORTED, "depthwise: op_size must be a multiple of the 128-bit channel vector");
+  int rc = check_fmap(ctx, in, op_size, rows, cols, "depthwise(in)");
+  if (rc) return rc;
+  rc = check_fmap(ctx, out, op_size, rows / stride, cols / stride, "depthwise(out)");
+  if (rc) return rc;
+  if (in->n != out->n) return fail(ctx, MNV1_EINVAL, "depthwise: batch mismatch");
+  TimedLaunch tl(ctx);
+  CK(ctx, run_depthwise(ctx, out->d, in->d, f, in->n, rows, cols, stride));
+  return MNV1_OK;
+}
+
+static int pointwise_impl(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* f, int rows,
+                          int cols, int filtersize, int op_size, bool force_simt) {
+  if (!ctx || !out || !in || !f) return fail(ctx, MNV1_EINVAL, "pointwise: null argument");
+  if ((f->kind != MNV1_POINTWISE && f->kind != MNV1_FC) || f->cout != op_size || f->cin != filtersize)
+    return fail(ctx, MNV1_EINVAL, "pointwise: filter mismatch (filtersize is the number of input planes, Cin)");
+  int rc = check_fmap(ctx, in, filtersize, rows, cols, "pointwise(in)");
+  if (rc) return rc;
+  rc = check_fmap(ctx, out, op_size, rows, cols, "pointwise(out)");
+  if (rc) return rc;
+  if (in->n != out->n) return fail(ctx, MNV1_EINVAL, "pointwise: batch mismatch");
+  TimedLaunch tl(ctx);
+  CK(ctx, run_pointwise(ctx, out->d, in->d, f, (long)in->n * rows * cols, force_simt));
+  return MNV1_OK;
+}
+int mnv1_pointwise(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* f, int rows, int cols,
+                   int filtersize, int op_size) {
+  return pointwise_impl(ctx, out, in, f, rows, cols, filtersize, op_size, false);
+}
+// the CUDA-core GEMM on any context (what fp32 contexts always run); used to cross-check the
+// tcgen05 kernel on the device
+int mnv1_pointwise_simt(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* f, int rows, int cols,
+                        int filtersize, int op_size) {
+  return pointwise_impl(ctx, out, in, f, rows, cols, filtersize, op_size, true);
+}
+
+int mnv1_pool(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, int rows, int cols, int filtersize, int op_size) {
+  if (!ctx || !out || !in) return fail(ctx, MNV1_EINVAL, "pool: null argument");
+  if (rows != filtersize || cols != filtersize)
+    return fail(ctx, MNV1_EUNSUPPORTED, "pool: global average only (rows = cols = filtersize, kernel.cl:126)");
+  if (op_size % 4) return fail(ctx, MNV1_EUNSUPPORTED, "pool: op_size must be a multiple of 4");
+  int rc = check_fmap(ctx, in, op_size, rows, cols, "pool(in)");
+  if (rc) return rc;
+  rc = check_fmap(ctx, out, op_size, 1, 1, "pool(out)");
+  if (rc) return rc;
+  if (in->n != out->n) return fail(ctx, MNV1_EINVAL, "pool: batch mismatch");
+  TimedLaunch tl(ctx);
+  ctx->launches++; ctx->last_kernel = "pool_kernel";
+  CK(ctx, mnv1::launch_pool(ctx->dtype, out->d, in->d, in->n, rows * cols, op_size, false, ctx->stream));
+  return MNV1_OK;
+}
+
+__global__ void widen_logits_kernel(float* out, const bf16* in, long n) {
+  long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+int mnv1_softmax(mnv1_ctx* ctx, const mnv1_buf* logits, int classes, float* prob, int* top1, float* top1_prob) {
+  if (!ctx || !logits || logits->is_u8 || logits->c != classes || logits->h != 1 || logits->w != 1)
+    return fail(ctx, MNV1_EINVAL, "softmax: logits must be [n][classes][1][1]");
+  const int n = logits->n;
+  if (n == 0) return MNV1_OK;
+  float *d_logits = nullptr, *d_prob = nullptr, *d_p1 = nullptr;
+  int* d_top1 = nullptr;
+  cudaError_t e = cudaSuccess;
+  const long cnt = (long)n * classes;
+  if (ctx->dtype == MNV1_BF16) {
+    e = cudaMalloc(&d_logits, cnt * 4);
+    if (e == cudaSuccess) {
+      widen_logits_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(d_logits, (const bf16*)logits->d, cnt);
+      ctx->launches++;
+    }
+  } else {
+    d_logits = (float*)logits->d;
+  }
+  if (e == cudaSuccess && prob) e = cudaMalloc(&d_prob, cnt * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_top1, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&d_p1, n * 4);
+  if (e == cudaSuccess) {
+    TimedLaunch tl(ctx);
+    ctx->launches++; ctx->last_kernel = "softmax_kernel";
+    e = mnv1::launch_softmax(d_logits, n, classes, d_prob, d_top1, d_p1, ctx->stream);
+  }
+  if (e == cudaSuccess && prob) e = cudaMemcpyAsync(prob, d_prob, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && top1) e = cudaMemcpyAsync(top1, d_top1, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && top1_prob) e = cudaMemcpyAsync(top1_prob, d_p1, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (ctx->dtype == MNV1_BF16) cudaFree(d_logits);
+  cudaFree(d_prob); cudaFree(d_top1); cudaFree(d_p1);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "softmax");
+  return MNV1_OK;
+}
+
+// ---------------------------------------------------------------- whole network
+int mnv1_layer_table(mnv1_layer_info* out) {
+  if (!out) return MNV1_EINVAL;
+  const LayerDef* L = layer_defs();
+  for (int i = 0; i < MNV1_NUM_LAYERS; ++i)
+    out[i] = {i + 1, L[i].kind, L[i].cin, L[i].cout, L[i].hin, L[i].hout, L[i].stride, L[i].w_off, L[i].w_cnt,
+              L[i].c_off};
+  return MNV1_OK;
+}
+
+int mnv1_set_weights(mnv1_ctx* ctx, const float* weights, const float* scale, const float* shift, mnv1_act act) {
+  if (!ctx || !weights) return fail(ctx, MNV1_EINVAL, "set_weights: null argument");
+  const LayerDef* L = layer_defs();
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  ctx->graphs.clear();
+  for (int i = 0; i < MNV1_NUM_LAYERS; ++i) {
+    if (ctx->net[i]) { mnv1_filter_destroy(ctx, ctx->net[i]); ctx->net[i] = nullptr; }
+    if (L[i].kind == MNV1_POOL) continue;
+    const bool fc = L[i].kind == MNV1_FC;
+    int rc = mnv1_filter_create(ctx, (mnv1_kind)L[i].kind, weights + L[i].w_off, L[i].cin, L[i].cout,
+                                (scale && !fc) ? scale + L[i].c_off : nullptr, shift ? shift + L[i].c_off : nullptr,
+                                fc ? MNV1_ACT_NONE : act, &ctx->net[i]);
+    if (rc) return rc;
+  }
+  ctx->have_weights = true;
+  return MNV1_OK;
+}
+
+int mnv1_load_weights(mnv1_ctx* ctx, const char* path, mnv1_act act) {
+  if (!ctx || !path) return fail(ctx, MNV1_EINVAL, "load_weights: null argument");
+  std::vector<float> w, sc, sh;
+  std::string err;
+  int rc = mnv1::load_weight_file(path, &w, &sc, &sh, &err);
+  if (rc) return fail(ctx, rc, err);
+  return mnv1_set_weights(ctx, w.data(), sc.data(), sh.data(), act);
+}
+int mnv1_save_weights_bin(const char* path, const float* weights, const float* scale, const float* shift) {
+  if (!path || !weights) return fail(nullptr, MNV1_EINVAL, "save_weights_bin: null argument");
+  std::string err;
+  int rc = mnv1::save_weight_file_bin(path, weights, scale, shift, &err);
+  if (rc) return fail(nullptr, rc, err);
+  return MNV1_OK;
+}
+int mnv1_read_ppm(const char* path, uint8_t* out, int height, int width) {
+  if (!path || !out) return fail(nullptr, MNV1_EINVAL, "read_ppm: null argument");
+  std::string err;
+  int rc = mnv1::read_ppm(path, out, height, width, &err);
+  if (rc) return fail(nullptr, rc, err);
+  return MNV1_OK;
+}
+
+static const size_t kImgBytes = 224 * 224 * 3;
+static const size_t kMaxActElems = 802816;  // layer 3 output per image (64 x 112 x 112)
+
+int mnv1_plan(mnv1_ctx* ctx, int max_batch) {
+  if (!ctx || max_batch <= 0) return fail(ctx, MNV1_EINVAL, "plan: bad batch");
+  if (max_batch <= ctx->plan_batch) return MNV1_OK;
+  cudaStreamSynchronize(ctx->stream);
+  free_plan(ctx);
+  const size_t act_bytes = (size_t)max_batch * kMaxActElems * elem_size(ctx->dtype);
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&ctx->act[i], act_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_images, (size_t)max_batch * kImgBytes);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_pooled, (size_t)max_batch * 1024 * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_logits, (size_t)max_batch * MNV1_NUM_CLASSES * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_top1, (size_t)max_batch * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_prob, (size_t)max_batch * 4);
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_images, (size_t)max_batch * kImgBytes);
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_logits, (size_t)max_batch * MNV1_NUM_CLASSES * 4);
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_top1, (size_t)max_batch * 4);
+  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_prob, (size_t)max_batch * 4);
+  if (e != cudaSuccess) {
+    free_plan(ctx);
+    return fail(ctx, MNV1_ENOMEM, std::string("plan: allocation failed: ") + cudaGetErrorString(e));
+  }
+  ctx->plan_batch = max_batch;
+  return MNV1_OK;
+}
+
+// Enqueue layers 1..last on the context stream.  Activations ping-pong between the two arena
+// halves; returns the device pointer holding layer `last`'s output in *result.
+static cudaError_t enqueue_layers(mnv1_ctx* ctx, const uint8_t* d_img, int n, int last, float* d_logits,
+                                  int* d_top1, float* d_prob, const void** result, cudaEvent_t* evs) {
+  const LayerDef* L = layer_defs();
+  const void* cur = nullptr;
+  int side = 0;
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < last && e == cudaSuccess; ++i) {
+    if (evs) cudaEventRecord(evs[i], ctx->stream);
+    void* dst = ctx->act[side];
+    const mnv1_filter* f = ctx->net[i];
+    switch (L[i].kind) {
+      case MNV1_CONVOLUTE:
+        e = run_stem(ctx, dst, d_img, d_img + 1, d_img + 2, 3, (long)kImgBytes, f, n, L[i].hin, L[i].hin, L[i].stride);
+        cur = dst; side ^= 1;
+        break;
+      case MNV1_DEPTHWISE:
+        e = run_depthwise(ctx, dst, cur, f, n, L[i].hin, L[i].hin, L[i].stride);
+        cur = dst; side ^= 1;
+        break;
+      case MNV1_POINTWISE:
+        e = run_pointwise(ctx, dst, cur, f, (long)n * L[i].hin * L[i].hin, false);
+        cur = dst; side ^= 1;
+        break;
+      case MNV1_POOL:
+        if (last == i + 1) {  // pool alone (per-layer dump): fp32 means
+          ctx->launches++; ctx->last_kernel = "pool_kernel";
+          e = mnv1::launch_pool(ctx->dtype, ctx->d_pooled, cur, n, L[i].hin * L[i].hin, L[i].cout, true, ctx->stream);
+          cur = ctx->d_pooled;
+        }
+        break;  // otherwise fused into the head below
+      case MNV1_FC: {
+        int nl = 0;
+        e = mnv1::launch_head(ctx->dtype, cur, n, 49, 1024, f, ctx->d_pooled, d_logits, d_top1, d_prob,
+                              MNV1_NUM_CLASSES, ctx->stream, &nl);
+        ctx->launches += nl; ctx->last_kernel = "head";
+        cur = d_logits;
+        break;
+      }
+    }
+  }
+  if (evs) cudaEventRecord(evs[last], ctx->stream);
+  if (result) *result = cur;
+  return e;
+}
+
+static int check_ready(mnv1_ctx* ctx, int n) {
+  if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
+  if (!ctx->have_weights) return fail(ctx, MNV1_ESTATE, "weights not loaded (mnv1_set_weights / mnv1_load_weights)");
+  if (n <= 0) return fail(ctx, MNV1_EINVAL, "batch must be positive");
+  if (n > ctx->plan_batch) {
+    int rc = mnv1_plan(ctx, n);
+    if (rc) return rc;
+  }
+  return MNV1_OK;
+}
+
+int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images, int n, void* d_logits, void* d_top1, void* d_prob) {
+  int rc = check_ready(ctx, n);
+  if (rc) return rc;
+  if (!d_images || !d_logits) return fail(ctx, MNV1_EINVAL, "forward_device: images and logits are required");
+  if (!ctx->use_graph) {
+    CK(ctx, enqueue_layers(ctx, (const uint8_t*)d_images, n, MNV1_NUM_LAYERS, (float*)d_logits, (int*)d_top1,
+                           (float*)d_prob, nullptr, nullptr));
+    return MNV1_OK;
+  }
+  GraphKey key{d_images, n, d_logits, d_top1, d_prob};
+  auto it = ctx->graphs.find(key);
+  if (it == ctx->graphs.end()) {
+    if (ctx->graphs.size() >= 16) {  // bounded cache
+      for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+      ctx->graphs.clear();
+    }
+    const long before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    CK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = enqueue_layers(ctx, (const uint8_t*)d_images, n, MNV1_NUM_LAYERS, (float*)d_logits, (int*)d_top1,
+                                   (float*)d_prob, nullptr, nullptr);
+    cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
+    ctx->launches = before;  // capture enqueues nothing
+    if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail_cuda(ctx, e, "graph capture (layer launch)"); }
+    if (e2 != cudaSuccess) return fail_cuda(ctx, e2, "cudaStreamEndCapture");
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaGraphInstantiate");
+    it = ctx->graphs.emplace(key, exec).first;
+  }
+  CK(ctx, cudaGraphLaunch(it->second, ctx->stream));
+  ctx->launches += 27 + ((d_top1 || d_prob) ? 3 : 2);
+  return MNV1_OK;
+}
+
+int mnv1_ctx_use_graph(mnv1_ctx* ctx, int on) {
+  if (!ctx) return MNV1_EINVAL;
+  ctx->use_graph = on != 0;
+  return MNV1_OK;
+}
+
+int mnv1_forward(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int* top1, float* top1_prob) {
+  int rc = check_ready(ctx, n);
+  if (rc) return rc;
+  if (!images) return fail(ctx, MNV1_EINVAL, "forward: images is null");
+  // stage through pinned memory unless the caller's buffer already is (cudaHostAlloc / cudaHostRegister)
+  cudaPointerAttributes pa;
+  const uint8_t* src = images;
+  if (cudaPointerGetAttributes(&pa, images) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+    cudaGetLastError();
+    memcpy(ctx->h_images, images, (size_t)n * kImgBytes);
+    src = ctx->h_images;
+  }
+  CK(ctx, cudaMemcpyAsync(ctx->d_images, src, (size_t)n * kImgBytes, cudaMemcpyHostToDevice, ctx->stream));
+  rc = mnv1_forward_device(ctx, ctx->d_images, n, ctx->d_logits, ctx->d_top1, ctx->d_prob);
+  if (rc) return rc;
+  if (logits) CK(ctx, cudaMemcpyAsync(ctx->h_logits, ctx->d_logits, (size_t)n * MNV1_NUM_CLASSES * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (top1) CK(ctx, cudaMemcpyAsync(ctx->h_top1, ctx->d_top1, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (top1_prob) CK(ctx, cudaMemcpyAsync(ctx->h_prob, ctx->d_prob, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (logits) memcpy(logits, ctx->h_logits, (size_t)n * MNV1_NUM_CLASSES * 4);
+  if (top1) memcpy(top1, ctx->h_top1, (size_t)n * 4);
+  if (top1_prob) memcpy(top1_prob, ctx->h_prob, (size_t)n * 4);
+  return MNV1_OK;
+}
+
+int mnv1_forward_upto(mnv1_ctx* ctx, const uint8_t* images, int n, int last_layer, float* host_nchw) {
+  int rc = check_ready(ctx, n);
+  if (rc) return rc;
+  if (!images || !host_nchw || last_layer < 1 || last_layer > MNV1_NUM_LAYERS)
+    return fail(ctx, MNV1_EINVAL, "forward_upto: bad arguments");
+  CK(ctx, cudaMemcpyAsync(ctx->d_images, images, (size_t)n * kImgBytes, cudaMemcpyHostToDevice, ctx->stream));
+  const void* res = nullptr;
+  CK(ctx, enqueue_layers(ctx, ctx->d_images, n, last_layer, ctx->d_logits, ctx->d_top1, ctx->d_prob, &res, nullptr));
+  const LayerDef& L = layer_defs()[last_layer - 1];
+  if (L.kind == MNV1_POOL || L.kind == MNV1_FC) {  // fp32 [n][C] already planar
+    CK(ctx, cudaMemcpyAsync(host_nchw, res, (size_t)n * L.cout * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return MNV1_OK;
+  }
+  mnv1_buf view;
+  view.d = const_cast<void*>(res); view.n = n; view.c = L.cout; view.h = L.hout; view.w = L.hout;
+  view.bytes = (size_t)n * L.cout * L.hout * L.hout * elem_size(ctx->dtype); view.owned = false;
+  return mnv1_download_planar(ctx, &view, host_nchw);
+}
+
+int mnv1_profile_layers(mnv1_ctx* ctx, const void* d_images, int n, int iters, float* times_ms) {
+  int rc = check_ready(ctx, n);
+  if (rc) return rc;
+  if (!d_images || !times_ms || iters <= 0) return fail(ctx, MNV1_EINVAL, "profile_layers: bad arguments");
+  cudaEvent_t evs[MNV1_NUM_LAYERS + 1];
+  for (auto& e : evs) CK(ctx, cudaEventCreate(&e));
+  for (int i = 0; i < MNV1_NUM_LAYERS; ++i) times_ms[i] = 0.f;
+  cudaError_t e = cudaSuccess;
+  for (int it = 0; it < iters + 1 && e == cudaSuccess; ++it) {  // first pass is a warm-up
+    e = enqueue_layers(ctx, (const uint8_t*)d_images, n, MNV1_NUM_LAYERS, ctx->d_logits, ctx->d_top1, ctx->d_prob,
+                       nullptr, evs);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && it > 0)
+      for (int i = 0; i < MNV1_NUM_LAYERS; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, evs[i], evs[i + 1]);
+        times_ms[i] += ms / iters;
+      }
+  }
+  for (auto& ev : evs) cudaEventDestroy(ev);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "profile_layers");
+  return MNV1_OK;
+}
+
+int mnv1_synth_images_device(mnv1_ctx* ctx, void* d_images, int n, long first, uint64_t seed) {
+  if (!ctx || !d_images || n < 0 || first < 0) return fail(ctx, MNV1_EINVAL, "synth_images: bad arguments");
+  ctx->launches++; ctx->last_kernel = "synth_images_kernel";
+  CK(ctx, mnv1::launch_synth_images((uint8_t*)d_images, first * (long)kImgBytes, (long)n * (long)kImgBytes, seed,
+                                    ctx->stream));
+  return MNV1_OK;
+}
+
+// pinned host memory for callers that want mnv1_forward to copy straight from their buffer
+// (CL_MEM_ALLOC_HOST_PTR analogue)
+int mnv1_host_alloc(size_t bytes, void** out) {
+  if (!out) return MNV1_EINVAL;
+  cudaError_t e = cudaMallocHost(out, bytes);
+  if (e != cudaSuccess) return fail(nullptr, MNV1_ENOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+  return MNV1_OK;
+}
+int mnv1_host_free(void* p) { cudaFreeHost(p); return MNV1_OK; }
+
+}  // extern "C"

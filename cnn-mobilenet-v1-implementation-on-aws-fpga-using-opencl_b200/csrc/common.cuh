@@ -1,0 +1,100 @@
+// common.cuh — internal types shared by the sm_100a kernels and the C-ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mnv1.h"
+
+typedef __nv_bfloat16 bf16;
+
+struct mnv1_buf {
+  void* d = nullptr;     // device storage
+  size_t bytes = 0;
+  int n = 0, c = 0, h = 0, w = 0;  // feature map (NHWC on the device); c==0 -> raw bytes
+  bool is_u8 = false;
+  bool owned = true;
+};
+
+struct mnv1_filter {
+  mnv1_kind kind;
+  int cin = 0, cout = 0;
+  mnv1_act act = MNV1_ACT_NONE;
+  float* w_f32 = nullptr;   // kernel-native fp32 copy (stem [27][Cout], dw [9][C], pw/fc [Cout][Cin])
+  bf16* w_bf16 = nullptr;   // bf16 [Cout][Cin] (pointwise / fc, bf16 contexts)
+  float* scale = nullptr;   // [Cout] or nullptr
+  float* shift = nullptr;   // [Cout] or nullptr
+  CUtensorMap tmap_b;       // TMA descriptor of w_bf16 (pointwise, bf16 contexts)
+  bool has_tmap = false;
+  int tmap_bn = 0;          // N-tile the descriptor's box was built for
+};
+
+struct Epilogue {
+  const float* scale;  // may be nullptr
+  const float* shift;  // may be nullptr
+  int act;
+};
+
+__device__ __forceinline__ float apply_epilogue(float acc, float s, float t, int act) {
+  float y = fmaf(acc, s, t);
+  if (act != MNV1_ACT_NONE) y = fmaxf(y, 0.0f);
+  if (act == MNV1_ACT_RELU6) y = fminf(y, 6.0f);
+  return y;
+}
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+
+// ---- launchers implemented in the .cu files (all asynchronous on `st`) -------------------
+namespace mnv1 {
+
+struct StemArgs {
+  const uint8_t *r, *g, *b;  // plane base pointers (interleaved: g = r+1, b = r+2)
+  int pix_stride;            // 1 planar, 3 interleaved
+  long img_stride;           // bytes between images for each pointer
+  int n, rows, cols, stride, cout, pad_lo;
+  float in_scale, in_bias;
+};
+cudaError_t launch_stem(mnv1_dtype dt, void* out, const StemArgs& a, const float* w27xC,
+                        Epilogue ep, cudaStream_t st);
+cudaError_t launch_depthwise(mnv1_dtype dt, void* out, const void* in, const float* w9xC, int n,
+                             int rows, int cols, int stride, int c, int pad_lo, Epilogue ep,
+                             cudaStream_t st);
+// generic SIMT 1x1 conv / FC: out[M][Cout] = in[M][K] * w[Cout][K]^T  (fp32 contexts, FC)
+cudaError_t launch_pointwise_simt(mnv1_dtype dt, void* out, const void* in, const float* w_f32,
+                                  const bf16* w_bf16, long m, int k, int cout, Epilogue ep,
+                                  bool out_f32, cudaStream_t st);
+// tcgen05 / TMEM / TMA 1x1 conv (bf16 contexts)
+cudaError_t launch_pointwise_tc(bf16* out, const bf16* in, const mnv1_filter* f, long m, int k,
+                                int cout, int num_sms, cudaStream_t st, std::string* err);
+cudaError_t make_weight_tmap(mnv1_filter* f, std::string* err);
+cudaError_t launch_pool(mnv1_dtype dt, void* out, const void* in, int n, int hw, int c, bool out_f32,
+                        cudaStream_t st);
+// fused head: global average pool -> FC (+bias) -> softmax -> argmax
+cudaError_t launch_head(mnv1_dtype dt, const void* in, int n, int hw, int c, const mnv1_filter* fc,
+                        float* pooled_scratch, float* logits, int* top1, float* top1_prob,
+                        int classes, cudaStream_t st, int* launches);
+cudaError_t launch_softmax(const float* logits, int n, int classes, float* prob, int* top1,
+                           float* top1_prob, cudaStream_t st);
+cudaError_t launch_nchw_to_nhwc(mnv1_dtype dt, void* out_nhwc, const float* in_nchw, int n, int c,
+                                int h, int w, cudaStream_t st);
+cudaError_t launch_nhwc_to_nchw(mnv1_dtype dt, float* out_nchw, const void* in_nhwc, int n, int c,
+                                int h, int w, cudaStream_t st);
+cudaError_t launch_synth_images(uint8_t* out, long first_byte, long nbytes, uint64_t seed,
+                                cudaStream_t st);
+}  // namespace mnv1

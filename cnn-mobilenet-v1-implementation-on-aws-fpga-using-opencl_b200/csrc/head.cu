@@ -1,0 +1,109 @@
+// head.cu — layers 28-30: global average pool, FC, softmax + argmax.
+//
+// Replaces `pool` (kernel.cl:116-131; MobileNet.c:2601-2679), the FC launch of `pointwise`
+// at rows=cols=1 (MobileNet.c:2681-2763) and the host softmax/argmax loop
+// (MobileNet.c:2769-2792).  Intended semantics: one mean per channel (App. C D-12), bias and
+// no activation on the logits (D-13), softmax with max subtraction, first maximum wins
+// (strict `>` at MobileNet.c:2786), 0-based index (the host prints index+1).
+#include "common.cuh"
+
+namespace mnv1 {
+
+cudaError_t launch_fc_f32in(float* out, const float* in, const float* w_f32, const bf16* w_bf16, long m, int k,
+                            int cout, Epilogue ep, cudaStream_t st);
+
+// in: NHWC [n][hw][c]; one thread per (image, channel pair/quad); lanes walk channels.
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) pool_kernel(TO* __restrict__ out, const T* __restrict__ in, int n, int hw,
+                                                   int c) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cq = c / 4;
+  if (idx >= (long)n * cq) return;
+  const int img = (int)(idx / cq), c0 = (int)(idx % cq) * 4;
+  const T* p = in + (long)img * hw * c + c0;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int i = 0; i < hw; ++i) {
+    if constexpr (sizeof(T) == 2) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (long)i * c));
+      s0 += bf16lo_to_f32(v.x); s1 += bf16hi_to_f32(v.x); s2 += bf16lo_to_f32(v.y); s3 += bf16hi_to_f32(v.y);
+    } else {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p + (long)i * c));
+      s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+    }
+  }
+  const float inv = 1.0f / (float)hw;
+  TO* o = out + (long)img * c + c0;
+  o[0] = from_f32<TO>(s0 * inv); o[1] = from_f32<TO>(s1 * inv);
+  o[2] = from_f32<TO>(s2 * inv); o[3] = from_f32<TO>(s3 * inv);
+}
+
+cudaError_t launch_pool(mnv1_dtype dt, void* out, const void* in, int n, int hw, int c, bool out_f32,
+                        cudaStream_t st) {
+  if (c % 4) return cudaErrorInvalidValue;
+  if (n <= 0) return cudaSuccess;
+  const long total = (long)n * (c / 4);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (dt == MNV1_F32) pool_kernel<float, float><<<grid, 256, 0, st>>>((float*)out, (const float*)in, n, hw, c);
+  else if (out_f32)   pool_kernel<bf16, float><<<grid, 256, 0, st>>>((float*)out, (const bf16*)in, n, hw, c);
+  else                pool_kernel<bf16, bf16><<<grid, 256, 0, st>>>((bf16*)out, (const bf16*)in, n, hw, c);
+  return cudaGetLastError();
+}
+
+// one warp per image: max / argmax, sum of exp, optional probabilities — warp shuffles only.
+__global__ void __launch_bounds__(128) softmax_kernel(const float* __restrict__ logits, int n, int classes,
+                                                      float* __restrict__ prob, int* __restrict__ top1,
+                                                      float* __restrict__ top1_prob) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  const float* z = logits + (long)warp * classes;
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int k = lane; k < classes; k += 32) {
+    const float v = z[k];
+    if (v > mx) { mx = v; arg = k; }  // per lane indices increase, so strict '>' keeps the first
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, off);
+    const int oarg = __shfl_xor_sync(0xffffffffu, arg, off);
+    if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
+  }
+  float sum = 0.f;
+  for (int k = lane; k < classes; k += 32) sum += __expf(z[k] - mx);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float inv = 1.0f / sum;
+  if (prob)
+    for (int k = lane; k < classes; k += 32) prob[(long)warp * classes + k] = __expf(z[k] - mx) * inv;
+  if (lane == 0) {
+    if (top1) top1[warp] = arg;
+    if (top1_prob) top1_prob[warp] = inv;
+  }
+}
+
+cudaError_t launch_softmax(const float* logits, int n, int classes, float* prob, int* top1, float* top1_prob,
+                           cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned grid = (unsigned)((n + 3) / 4);
+  softmax_kernel<<<grid, 128, 0, st>>>(logits, n, classes, prob, top1, top1_prob);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_head(mnv1_dtype dt, const void* in, int n, int hw, int c, const mnv1_filter* fc,
+                        float* pooled_scratch, float* logits, int* top1, float* top1_prob, int classes,
+                        cudaStream_t st, int* launches) {
+  cudaError_t e = launch_pool(dt, pooled_scratch, in, n, hw, c, /*out_f32=*/true, st);
+  if (e != cudaSuccess) return e;
+  Epilogue ep{nullptr, fc->shift, MNV1_ACT_NONE};
+  e = launch_fc_f32in(logits, pooled_scratch, fc->w_f32, dt == MNV1_BF16 ? fc->w_bf16 : nullptr, n, c, classes,
+                      ep, st);
+  if (e != cudaSuccess) return e;
+  if (launches) *launches = 2;
+  if (top1 || top1_prob) {
+    e = launch_softmax(logits, n, classes, nullptr, top1, top1_prob, st);
+    if (launches) *launches = 3;
+  }
+  return e;
+}
+
+}  // namespace mnv1

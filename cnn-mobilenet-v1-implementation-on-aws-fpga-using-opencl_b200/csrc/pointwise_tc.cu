@@ -1,0 +1,370 @@
+// pointwise_tc.cu — 1x1 convolution on the 5th-gen tensor cores (tcgen05 / TMEM / TMA).
+//
+// Replaces `pointwise` (kernel.cl:94-114; 13 launches) for bf16 contexts:
+//   out[M][Cout] = act( scale * (in[M][K] . w[Cout][K]^T) + shift ),  M = N*H*W, K = Cin.
+// The NHWC feature map IS the K-major A operand and the reference's [Cout][Cin] filter order
+// (kernel.cl:106) IS the K-major B operand, so neither is re-laid out.
+//
+// Persistent, warp-specialised CTA (one per SM), 192 threads:
+//   warp 0      TMA producer: A tile 128 x 64 and B tile BN x 64 (bf16, 128B swizzle) per k-block
+//               into a ring of `stages` shared-memory slots (full/empty mbarriers)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32
+//               accumulators in TMEM, two accumulator stages so the epilogue of tile i overlaps
+//               the MMAs of tile i+1)
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> scale/shift/ReLU6 -> bf16 -> 16-byte
+//               global stores of each thread's output row
+// K tails (K = 32 < 64) and M tails are zero-filled by TMA out-of-bounds handling; stores are
+// masked by row.
+#include "common.cuh"
+
+#include <cstdio>
+
+namespace mnv1 {
+
+namespace {
+
+constexpr int TC_BM = 128;       // UMMA M (cta_group::1)
+constexpr int TC_BK = 64;        // bf16 elements per k-block = 128 bytes = one swizzle row
+constexpr int TC_UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_MAX_COUT = 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (SM100 UMMA SmemDescriptor):
+// start address >> 4 in bits [0,14), LBO (unused for swizzled K-major, = 1) in [16,30),
+// SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1),
+// both K-major (bits 15,16 = 0), N >> 3 in bits [17,23), M >> 4 in bits [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct __align__(8) TcBarriers {
+  uint64_t full[TC_MAX_STAGES];
+  uint64_t empty[TC_MAX_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    bf16* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
+                    int act, long M, int K, int Cout, int stages) {
+  constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+  constexpr uint32_t B_BYTES = BN * TC_BK * 2;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BN;            // two accumulator stages (power of two >= 32)
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "tmem cols");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A | B)] 1024-aligned, then scale/shift, then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_scale = reinterpret_cast<float*>(smem + (size_t)stages * STAGE_BYTES);
+  float* s_shift = s_scale + TC_MAX_COUT;
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(s_shift + TC_MAX_COUT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = Cout / BN;
+  const long m_tiles = (M + TC_BM - 1) / TC_BM;
+  const long num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+
+  for (int i = threadIdx.x; i < Cout; i += TC_THREADS) {
+    s_scale[i] = scale ? scale[i] : 1.f;
+    s_shift[i] = shift ? shift[i] : 0.f;
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    for (int s = 0; s < stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_idx = (int)(t / n_tiles) * TC_BM, n_idx = (int)(t % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1u);
+          uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+          mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tmap_a, &bars->full[stage], kb * TC_BK, m_idx);
+          tma_load_2d(sa + A_BYTES, &tmap_b, &bars->full[stage], kb * TC_BK, n_idx);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (one thread) =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN);
+      int stage = 0; uint32_t phase = 0;
+      int as = 0; uint32_t aphase = 0;
+      for (long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);          // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+            // advance 16 elements = 32 bytes inside the 128B swizzle row: +2 in the (>>4) address field
+            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&bars->empty[stage]);              // frees the smem slot when these MMAs retire
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&bars->tmem_full[as]);               // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    }
+  } else {
+    // ================= epilogue warps 2..5 =================
+    const int quarter = warp & 3;                        // TMEM lanes 32*quarter .. +31 belong to this warp
+    int as = 0; uint32_t aphase = 0;
+    for (long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const long m_idx = (t / n_tiles) * TC_BM;
+      const int n_idx = (int)(t % n_tiles) * BN;
+      mbar_wait(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+      const long row = m_idx + quarter * 32 + lane;
+      bf16* orow = out + row * Cout + n_idx;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[n_idx + c0 + j]);
+          const float4 t4 = *reinterpret_cast<const float4*>(&s_shift[n_idx + c0 + j]);
+          const float y0 = apply_epilogue(__uint_as_float(v[j + 0]), s4.x, t4.x, act);
+          const float y1 = apply_epilogue(__uint_as_float(v[j + 1]), s4.y, t4.y, act);
+          const float y2 = apply_epilogue(__uint_as_float(v[j + 2]), s4.z, t4.z, act);
+          const float y3 = apply_epilogue(__uint_as_float(v[j + 3]), s4.w, t4.w, act);
+          packed[j / 2] = pack_bf16x2(y0, y1);
+          packed[j / 2 + 1] = pack_bf16x2(y2, y3);
+        }
+        if (row < M) {
+          uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o4[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn(std::string* err) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    if (err) *err = "cuTensorMapEncodeTiled entry point not available";
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D bf16 tensor [rows][k] (k contiguous) with a (64 x box_rows) box and 128B swizzle.
+cudaError_t encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t k, uint32_t box_rows,
+                      std::string* err) {
+  EncodeTiledFn fn = get_encode_fn(err);
+  if (!fn) return cudaErrorNotSupported;
+  cuuint64_t gdim[2] = {k, rows};
+  cuuint64_t gstride[1] = {k * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) {
+      char b[160];
+      snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (CUresult %d) rows=%llu k=%llu box_rows=%u", (int)r,
+               (unsigned long long)rows, (unsigned long long)k, box_rows);
+      *err = b;
+    }
+    return cudaErrorInvalidValue;
+  }
+  return cudaSuccess;
+}
+
+int pick_bn(int cout) {
+  if (cout % 256 == 0) return 256;
+  if (cout % 128 == 0) return 128;
+  if (cout % 64 == 0) return 64;
+  if (cout % 32 == 0) return 32;
+  return 0;
+}
+
+template <int BN>
+cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, const float* scale,
+                      const float* shift, int act, long m, int k, int cout, int num_sms, cudaStream_t st) {
+  const int num_kb = (k + TC_BK - 1) / TC_BK;
+  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2;
+  const size_t fixed = 1024 /*align slack*/ + 2 * TC_MAX_COUT * sizeof(float) + sizeof(TcBarriers);
+  int stages = (int)((227 * 1024 - fixed) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  // a ring deeper than ~2 tiles' worth of k-blocks only costs smem; keep at least 2
+  int want = 2 * num_kb < 4 ? 4 : 2 * num_kb;
+  if (stages > want) stages = want;
+  if (stages < 2) return cudaErrorInvalidValue;
+  const size_t smem = fixed + stages * stage_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(pointwise_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const long tiles = ((m + TC_BM - 1) / TC_BM) * (cout / BN);
+  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+  pointwise_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(ta, tb, out, scale, shift, act, m, k, cout, stages);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t make_weight_tmap(mnv1_filter* f, std::string* err) {
+  const int bn = pick_bn(f->cout);
+  if (!bn || f->cin % 8 || f->cout > TC_MAX_COUT) {
+    if (err) *err = "pointwise tcgen05 path needs Cout % 32 == 0, Cout <= 1024 and Cin % 8 == 0";
+    return cudaErrorInvalidValue;
+  }
+  cudaError_t e = encode_2d(&f->tmap_b, f->w_bf16, (uint64_t)f->cout, (uint64_t)f->cin, (uint32_t)bn, err);
+  if (e == cudaSuccess) { f->has_tmap = true; f->tmap_bn = bn; }
+  return e;
+}
+
+cudaError_t launch_pointwise_tc(bf16* out, const bf16* in, const mnv1_filter* f, long m, int k, int cout,
+                                int num_sms, cudaStream_t st, std::string* err) {
+  if (!f->has_tmap || k != f->cin || cout != f->cout) {
+    if (err) *err = "pointwise_tc: filter has no TMA descriptor or shape mismatch";
+    return cudaErrorInvalidValue;
+  }
+  if (m <= 0) return cudaSuccess;
+  CUtensorMap ta;
+  cudaError_t e = encode_2d(&ta, in, (uint64_t)m, (uint64_t)k, TC_BM, err);
+  if (e != cudaSuccess) return e;
+  switch (f->tmap_bn) {
+    case 256: return launch_bn<256>(ta, f->tmap_b, out, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
+    case 128: return launch_bn<128>(ta, f->tmap_b, out, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
+    case 64:  return launch_bn<64>(ta, f->tmap_b, out, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
+    case 32:  return launch_bn<32>(ta, f->tmap_b, out, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace mnv1

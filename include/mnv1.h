@@ -1,0 +1,176 @@
+/*
+ * mnv1.h — C-ABI of the B200-native MobileNet-V1 1.0-224 inference path.
+ *
+ * Drop-in boundary for the reference's host programs (MobileNet.c, MobileNet_13Layers.c,
+ * MobileNet_L5.c).  The reference has no library API; its seam is the OpenCL host call
+ * sequence repeated for every layer (MobileNet.c:322-408 is one instance) plus the four
+ * kernel argument lists of kernel.cl.  Each entry point below names the reference lines it
+ * replaces.  Plain C: opaque handles, plain pointers and sizes, int error codes, no
+ * exceptions cross the boundary.  INTEGRATION.md shows the edits a maintainer makes in
+ * MobileNet.c to bind to it.
+ *
+ * Conventions
+ *  - every function returns 0 (MNV1_OK) or a negative MNV1_E* code; mnv1_last_error()
+ *    gives the text (the reference's `printf("Error: ...") ; exit(1)` stays at the call site)
+ *  - host tensors use the reference's layout: planar [N][C][H][W]
+ *    (kernel.cl:14,56,73,90,103,107), filters OIHW / [C][3][3] / [Cout][Cin] in `findex`
+ *    order (kernel.cl:18,30,42,77,106).  Device tensors are opaque (NHWC inside).
+ *  - launches are asynchronous on the context's stream; download / softmax / forward /
+ *    *_time_ms synchronise.  One context per GPU; a context is not thread-safe.
+ */
+#ifndef MNV1_H
+#define MNV1_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNV1_OK 0
+#define MNV1_EINVAL (-1)       /* bad argument / shape mismatch                         */
+#define MNV1_ECUDA (-2)        /* CUDA runtime or driver error (see mnv1_last_error)     */
+#define MNV1_ENOMEM (-3)       /* host or device allocation failed                      */
+#define MNV1_EIO (-4)          /* weight / image file could not be read                 */
+#define MNV1_ESTATE (-5)       /* call order: weights not loaded, plan missing, ...      */
+#define MNV1_EUNSUPPORTED (-6) /* shape outside what the sm_100a kernels implement       */
+
+typedef enum { MNV1_F32 = 0, MNV1_BF16 = 1 } mnv1_dtype;
+typedef enum { MNV1_ACT_NONE = 0, MNV1_ACT_RELU = 1, MNV1_ACT_RELU6 = 2 } mnv1_act;
+/* padding of stride-2 layers: REF = 1 px top/left (kernel.cl:20,79 `< 0` test),
+ * TFSAME = Keras/TF "SAME" on even sizes (0 top/left, 1 bottom/right). Stride 1: 1 px all round. */
+typedef enum { MNV1_PAD_REF = 0, MNV1_PAD_TFSAME = 1 } mnv1_pad;
+typedef enum {
+  MNV1_CONVOLUTE = 0, /* kernel.cl:2   */
+  MNV1_DEPTHWISE = 1, /* kernel.cl:62  */
+  MNV1_POINTWISE = 2, /* kernel.cl:94  */
+  MNV1_POOL = 3,      /* kernel.cl:116 */
+  MNV1_FC = 4         /* pointwise reused at 1x1, MobileNet.c:2689 */
+} mnv1_kind;
+
+typedef struct mnv1_ctx mnv1_ctx;       /* replaces cl_context + cl_command_queue + cl_program */
+typedef struct mnv1_buf mnv1_buf;       /* replaces cl_mem for images / feature maps           */
+typedef struct mnv1_filter mnv1_filter; /* replaces cl_mem d_filter (+ folded BN, activation)  */
+
+/* ---- context: replaces platform/device/context/queue/program bring-up (MobileNet.c:147-205)
+ *      and the release calls (MobileNet.c:2809-2831) --------------------------------------- */
+int mnv1_ctx_create(int device, mnv1_dtype dtype, mnv1_ctx** ctx);
+int mnv1_ctx_destroy(mnv1_ctx* ctx);
+const char* mnv1_last_error(const mnv1_ctx* ctx); /* ctx may be NULL (creation failures) */
+int mnv1_ctx_set_stream(mnv1_ctx* ctx, void* cuda_stream);  /* cudaStream_t owned by the caller */
+int mnv1_ctx_set_pad_mode(mnv1_ctx* ctx, mnv1_pad pad);     /* default MNV1_PAD_REF */
+/* stem maps every u8 pixel x -> x*scale + bias before the conv; default 1, 0 (raw integers,
+ * as kernel.cl reads them); Keras MobileNet preprocessing is 1/127.5, -1 */
+int mnv1_ctx_set_input_transform(mnv1_ctx* ctx, float scale, float bias);
+int mnv1_sync(mnv1_ctx* ctx);                               /* clFinish, MobileNet.c:302 */
+/* device time of the most recent kernel launched through this context, in ms: replaces
+ * clGetEventProfilingInfo(COMMAND_START/END), MobileNet.c:303-305 (which prints seconds) */
+int mnv1_last_kernel_ms(mnv1_ctx* ctx, float* ms);
+int mnv1_ctx_enable_timing(mnv1_ctx* ctx, int on); /* default on; off removes the event pair */
+
+/* ---- buffers: replace clCreateBuffer / clEnqueueWriteBuffer / clEnqueueReadBuffer
+ *      (MobileNet.c:340-342,350-351,395) ---------------------------------------------------- */
+int mnv1_malloc(mnv1_ctx* ctx, int n, int c, int h, int w, mnv1_buf** buf); /* feature map */
+int mnv1_malloc_u8(mnv1_ctx* ctx, size_t bytes, mnv1_buf** buf);            /* image planes */
+int mnv1_free(mnv1_ctx* ctx, mnv1_buf* buf);
+int mnv1_upload_u8(mnv1_ctx* ctx, mnv1_buf* buf, const uint8_t* host, size_t bytes);
+int mnv1_upload_planar(mnv1_ctx* ctx, mnv1_buf* buf, const float* host_nchw);
+int mnv1_download_planar(mnv1_ctx* ctx, mnv1_buf* buf, float* host_nchw);
+void* mnv1_buf_device_ptr(mnv1_buf* buf);
+
+/* ---- filters: replace readSquezeNetKernel + clCreateBuffer(d_filter) (MobileNet.c:31-47,
+ *      241,248).  `w` is in the reference's flat order for that kernel kind; scale/shift
+ *      (per output channel, may be NULL) are a folded BatchNorm or, for MNV1_FC, the bias. -- */
+int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, int cout,
+                       const float* scale, const float* shift, mnv1_act act,
+                       mnv1_filter** filter);
+int mnv1_filter_destroy(mnv1_ctx* ctx, mnv1_filter* filter);
+
+/* ---- the four kernels; after `ctx` the argument order is kernel.cl's --------------------- */
+/* kernel.cl:2-3 / clSetKernelArg at MobileNet.c:272-281.  in_r/g/b: u8 planes [n][rows][cols];
+ * out: [n][op_size][rows/stride][cols/stride]. */
+int mnv1_convolute(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in_r, const mnv1_buf* in_g,
+                   const mnv1_buf* in_b, const mnv1_filter* filter, int rows, int cols,
+                   int filtersize, int stride, int op_size);
+/* same, on the interleaved RGB payload `image[]` (MobileNet.c:29) without the host-side split
+ * of MobileNet.c:218-238: in_rgb is u8 [n][rows][cols][3] */
+int mnv1_convolute_rgb(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in_rgb,
+                       const mnv1_filter* filter, int rows, int cols, int filtersize, int stride,
+                       int op_size);
+/* kernel.cl:62 / MobileNet.c:363-370 */
+int mnv1_depthwise(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* filter,
+                   int rows, int cols, int filtersize, int stride, int op_size);
+/* kernel.cl:94 / MobileNet.c:453-459.  filtersize = number of input planes contracted (Cin);
+ * the reference passes K_P = 1 — pass Cin. Also the FC layer (rows=cols=1). */
+int mnv1_pointwise(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* filter,
+                   int rows, int cols, int filtersize, int op_size);
+/* kernel.cl:116 / MobileNet.c:2640-2645.  filtersize x filtersize global average. */
+int mnv1_pool(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, int rows, int cols,
+              int filtersize, int op_size);
+/* host softmax + argmax of MobileNet.c:2769-2792, on the device.  logits: [n][classes][1][1].
+ * prob [n][classes] / top1 [n] (0-based; the reference prints location = index + 1) /
+ * top1_prob [n] are host arrays, any may be NULL. */
+int mnv1_softmax(mnv1_ctx* ctx, const mnv1_buf* logits, int classes, float* prob, int* top1,
+                 float* top1_prob);
+
+/* ---- whole network: the 29-block schedule of MobileNet.c:207-2763 in one call ------------- */
+#define MNV1_NUM_LAYERS 29
+#define MNV1_NUM_CLASSES 1000
+#define MNV1_TOTAL_WEIGHTS 4209088L /* sum of the readSquezeNetKernel counts, SURVEY App. A */
+#define MNV1_BN_CHANNELS 10944L
+typedef struct {
+  int index, kind, cin, cout, hin, hout, stride;
+  long w_off, w_cnt, c_off;
+} mnv1_layer_info;
+int mnv1_layer_table(mnv1_layer_info* out29);
+/* weights: MNV1_TOTAL_WEIGHTS floats in file order; scale/shift: MNV1_BN_CHANNELS + 1000
+ * (last 1000 = FC bias in shift), may be NULL (=1 / =0).  Replaces the 29 readSquezeNetKernel
+ * calls.  act applies to layers 1-27. */
+int mnv1_set_weights(mnv1_ctx* ctx, const float* weights, const float* scale, const float* shift,
+                     mnv1_act act);
+/* weight file: either the reference's text format (whitespace separated decimals,
+ * MobileNet.c:37-44, read sequentially instead of re-opened per layer) or "MNV1WTS1" binary
+ * (see csrc/weights_io.cpp).  A file with only MNV1_TOTAL_WEIGHTS values gets scale=1, shift=0. */
+int mnv1_load_weights(mnv1_ctx* ctx, const char* path, mnv1_act act);
+int mnv1_save_weights_bin(const char* path, const float* weights, const float* scale,
+                          const float* shift);
+/* P6 PPM reader that skips the header (fixes SURVEY App. C D-15); out = 224*224*3 bytes */
+int mnv1_read_ppm(const char* path, uint8_t* out_rgb, int height, int width);
+/* allocate the activation arena for batches up to max_batch and capture the CUDA graph */
+int mnv1_plan(mnv1_ctx* ctx, int max_batch);
+/* host in, host out.  images: u8 [n][224][224][3] (PPM payload order); logits [n][1000] fp32,
+ * top1 [n], top1_prob [n] — any output may be NULL.  Includes H2D, the 28 launches, D2H. */
+int mnv1_forward(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int* top1,
+                 float* top1_prob);
+/* device in, device out, asynchronous on the context stream (no copies, no sync) */
+int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images_u8, int n, void* d_logits_f32,
+                        void* d_top1_i32, void* d_top1_prob_f32);
+/* run layers 1..last_layer eagerly and copy layer `last_layer`'s output to host planar fp32
+ * (the per-layer parity dump; configs "first 5 layers" / "first 13 layers") */
+int mnv1_forward_upto(mnv1_ctx* ctx, const uint8_t* images, int n, int last_layer,
+                      float* host_nchw);
+/* per-layer device time (ms) of the last mnv1_profile_layers run; times[29] */
+int mnv1_profile_layers(mnv1_ctx* ctx, const void* d_images_u8, int n, int iters, float* times_ms);
+/* fill d_images (u8 [n][224][224][3]) with the synthetic stream of SURVEY §8(d): images
+ * first..first+n-1 of seed `seed`, generated on the device */
+int mnv1_synth_images_device(mnv1_ctx* ctx, void* d_images_u8, int n, long first, uint64_t seed);
+/* number of kernels launched through this context so far (bench.py's gpu_launches) */
+long mnv1_launch_count(const mnv1_ctx* ctx);
+/* name of the kernel the most recent entry point launched ("pointwise_tc_kernel", ...) */
+const char* mnv1_last_kernel_name(const mnv1_ctx* ctx);
+/* the CUDA-core GEMM that fp32 contexts always use, callable on any context: lets a test
+ * cross-check the tcgen05 kernel on the device.  Same arguments as mnv1_pointwise. */
+int mnv1_pointwise_simt(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* filter,
+                        int rows, int cols, int filtersize, int op_size);
+/* 1 (default): mnv1_forward* replays a captured CUDA graph; 0: launches the kernels eagerly */
+int mnv1_ctx_use_graph(mnv1_ctx* ctx, int on);
+/* page-locked host memory (CL_MEM_ALLOC_HOST_PTR analogue): mnv1_forward copies straight
+ * from / to such buffers instead of staging */
+int mnv1_host_alloc(size_t bytes, void** out);
+int mnv1_host_free(void* p);
+const char* mnv1_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MNV1_H */

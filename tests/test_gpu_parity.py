@@ -1,0 +1,316 @@
+"""GPU parity tests: CUDA kernels (through the C-ABI, via ctypes) vs the CPU oracle.
+
+Bars (BASELINE.json north_star): integer KATs bit-exact; fp32 within 1e-4 relative per layer
+(|a-b| <= 1e-4 * max(1,|b|)); bf16 within one bf16 ulp per layer when both sides get the same
+input (|a-b| <= 2^-7 * max(1,|b|)), looser and stated for the end-to-end network.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2.0 ** -7
+
+
+@pytest.fixture(scope="module")
+def mn():
+    import mnv1_b200  # noqa: F401
+    from mnv1_b200 import binding
+    return binding
+
+
+@pytest.fixture(scope="module", params=["f32", "bf16"])
+def ctx(request, mn):
+    c = mn.Context(0, mn.F32 if request.param == "f32" else mn.BF16)
+    yield c
+    c.close()
+
+
+def _ints(seed, shape, lo, hi):
+    from mnv1_b200 import synth
+    return synth.kat_ints(seed, int(np.prod(shape)), lo, hi).reshape(shape)
+
+
+# --------------------------------------------------------------------------- KATs (exact)
+@pytest.mark.parametrize("c,h", [(8, 14), (32, 28), (64, 7)])
+def test_kat_depthwise_three_way(ctx, mn, oracle_mod, c, h):
+    """kernel.cl `depthwise` (per-channel launches) == oracle == CUDA, bit for bit."""
+    x = _ints(1, (c, h, h), 0, 3).astype(np.uint8)
+    w = _ints(2, (c, 3, 3), -2, 2).astype(np.int32)
+    want = oracle_mod.depthwise(x[None].astype(np.float32), w.astype(np.float32), 1, act=oracle_mod.ACT_RELU)
+    lit = oracle_mod.lit_depthwise_per_channel(x, w, 1) if oracle_mod.literal() else None
+    if lit is not None:  # literal is valid for x < cols-1 (right column wraps, App. C D-08)
+        assert np.array_equal(lit[:, :, :-1].astype(np.float32), want[0, :, :, :-1])
+    f = ctx.filter(mn.DEPTHWISE, w.astype(np.float32), c, c, act=mn.ACT_RELU)
+    xin = ctx.upload_planar(x[None].astype(np.float32))
+    out = ctx.malloc(1, c, h, h)
+    ctx.depthwise(out, xin, f, h, h, 3, 1, c)
+    got = ctx.download_planar(out)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("cin,cout,h,hi", [(32, 64, 14, 3), (64, 128, 7, 1), (8, 16, 5, 3), (128, 256, 12, 1)])
+def test_kat_pointwise_three_way(ctx, mn, oracle_mod, cin, cout, h, hi):
+    """kernel.cl `pointwise` (filtersize = Cin) == oracle == CUDA (tcgen05 on bf16 contexts)."""
+    x = _ints(3, (cin, h, h), 0, hi).astype(np.uint8)
+    w = _ints(4, (cout, cin), -1, 1).astype(np.int32)
+    want = oracle_mod.pointwise(x[None].astype(np.float32), w.astype(np.float32), cout, act=oracle_mod.ACT_RELU)
+    assert want.max() < 256
+    if oracle_mod.literal():
+        lit = oracle_mod.lit_pointwise_per_channel(x, w)
+        assert np.array_equal(lit.astype(np.float32), want[0])
+    f = ctx.filter(mn.POINTWISE, w.astype(np.float32), cin, cout, act=mn.ACT_RELU)
+    xin = ctx.upload_planar(x[None].astype(np.float32))
+    out = ctx.malloc(1, cout, h, h)
+    ctx.pointwise(out, xin, f, h, h, cin, cout)
+    got = ctx.download_planar(out)
+    if ctx.dtype == mn.BF16 and cout % 32 == 0 and cin % 8 == 0:
+        assert ctx.last_kernel_name == "pointwise_tc_kernel"
+    assert np.array_equal(got, want)
+
+
+def test_kat_pool_three_way(ctx, mn, oracle_mod):
+    c = 64
+    x = (_ints(5, (c, 7, 7), 0, 4) * 49 // 4).astype(np.uint8)  # any u8; compare the means
+    x = _ints(5, (c, 7, 7), 0, 5).astype(np.uint8)
+    x[:, :, :] = x[:, :1, :1]  # constant planes: the mean is an exact integer in every dtype
+    want = oracle_mod.pool(x[None].astype(np.float32), truncate=True)
+    if oracle_mod.literal():
+        assert np.array_equal(oracle_mod.lit_pool_per_channel(x).astype(np.float32), want[0])
+    xin = ctx.upload_planar(x[None].astype(np.float32))
+    out = ctx.malloc(1, c, 1, 1)
+    ctx.pool(out, xin, 7, 7, 7, c)
+    got = ctx.download_planar(out).reshape(1, c)
+    assert np.array_equal(got, want)
+
+
+# --------------------------------------------------------------------------- per-layer parity
+def _tol(ctx, mn):
+    return FP32_TOL if ctx.dtype == mn.F32 else BF16_TOL
+
+
+def _prep(ctx, mn, oracle_mod, x):
+    """What the device will actually hold: bf16 contexts round the activations on upload."""
+    return oracle_mod.round_bf16(x) if ctx.dtype == mn.BF16 else x
+
+
+@pytest.mark.parametrize("c,h,stride,pad", [(32, 112, 1, 0), (64, 112, 2, 0), (64, 112, 2, 1), (128, 56, 1, 1),
+                                            (256, 28, 2, 1), (512, 14, 1, 0), (512, 14, 2, 1), (1024, 7, 1, 0),
+                                            (16, 10, 2, 0), (8, 9, 1, 0)])
+def test_depthwise_layer(ctx, mn, oracle_mod, c, h, stride, pad):
+    if h % stride:
+        pytest.skip("odd size with stride 2")
+    rng = np.random.default_rng(10 + c + h)
+    n = 2
+    x = _prep(ctx, mn, oracle_mod, (rng.random((n, c, h, h), dtype=np.float32) * 6))
+    w = rng.standard_normal((c, 3, 3)).astype(np.float32) * 0.5
+    sc = (0.5 + rng.random(c)).astype(np.float32)
+    sh = (rng.standard_normal(c) * 0.1).astype(np.float32)
+    want = oracle_mod.depthwise(x, w, stride, pad_mode=pad, scale=sc, shift=sh, act=oracle_mod.ACT_RELU6,
+                                rbf16=ctx.dtype == mn.BF16)
+    ctx.set_pad_mode(pad)
+    f = ctx.filter(mn.DEPTHWISE, w, c, c, sc, sh, mn.ACT_RELU6)
+    xin = ctx.upload_planar(x)
+    out = ctx.malloc(n, c, h // stride, h // stride)
+    ctx.depthwise(out, xin, f, h, h, 3, stride, c)
+    got = ctx.download_planar(out)
+    ctx.set_pad_mode(mn.PAD_REF)
+    assert rel_err(got, want) <= _tol(ctx, mn)
+
+
+@pytest.mark.parametrize("cin,cout,h,n", [(32, 64, 112, 1), (64, 128, 56, 2), (128, 128, 56, 1), (128, 256, 28, 3),
+                                          (256, 256, 28, 1), (256, 512, 14, 2), (512, 512, 14, 5), (512, 1024, 7, 3),
+                                          (1024, 1024, 7, 2), (24, 40, 5, 1)])
+def test_pointwise_layer(ctx, mn, oracle_mod, cin, cout, h, n):
+    rng = np.random.default_rng(20 + cin + cout)
+    x = _prep(ctx, mn, oracle_mod, rng.random((n, cin, h, h), dtype=np.float32) * 6)
+    w = (rng.standard_normal((cout, cin)) * np.sqrt(2.0 / cin)).astype(np.float32)
+    if ctx.dtype == mn.BF16:
+        w = oracle_mod.round_bf16(w)
+    sc = (0.5 + rng.random(cout)).astype(np.float32)
+    sh = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    want = oracle_mod.pointwise(x, w, cout, scale=sc, shift=sh, act=oracle_mod.ACT_RELU6, rbf16=ctx.dtype == mn.BF16)
+    f = ctx.filter(mn.POINTWISE, w, cin, cout, sc, sh, mn.ACT_RELU6)
+    xin = ctx.upload_planar(x)
+    out = ctx.malloc(n, cout, h, h)
+    ctx.pointwise(out, xin, f, h, h, cin, cout)
+    got = ctx.download_planar(out)
+    assert rel_err(got, want) <= _tol(ctx, mn)
+    if ctx.dtype == mn.BF16 and cout % 32 == 0 and cin % 8 == 0:
+        assert ctx.last_kernel_name == "pointwise_tc_kernel"
+        # the CUDA-core GEMM must agree with the tensor-core one to the same tolerance
+        out2 = ctx.malloc(n, cout, h, h)
+        ctx.pointwise(out2, xin, f, h, h, cin, cout, simt=True)
+        assert rel_err(ctx.download_planar(out2), want) <= _tol(ctx, mn)
+
+
+@pytest.mark.parametrize("pad", [0, 1])
+def test_stem_layer(ctx, mn, oracle_mod, pad):
+    from mnv1_b200 import synth
+    rng = np.random.default_rng(30)
+    n = 2
+    img = synth.images(n)
+    w = (rng.standard_normal((32, 3, 3, 3)) * np.sqrt(2.0 / 27)).astype(np.float32)
+    sc = (0.5 + rng.random(32)).astype(np.float32)
+    sh = (rng.standard_normal(32) * 0.1).astype(np.float32)
+    want = oracle_mod.convolute(img, img.reshape(-1)[1:], img.reshape(-1)[2:], w, n, 224, 224, 2, 32, pad_mode=pad,
+                                in_scale=1 / 127.5, in_bias=-1.0, scale=sc, shift=sh, act=oracle_mod.ACT_RELU6,
+                                rbf16=ctx.dtype == mn.BF16, pix_stride=3, img_stride=224 * 224 * 3)
+    ctx.set_pad_mode(pad)
+    ctx.set_input_transform(1 / 127.5, -1.0)
+    f = ctx.filter(mn.CONVOLUTE, w, 3, 32, sc, sh, mn.ACT_RELU6)
+    out = ctx.malloc(n, 32, 112, 112)
+    rgb = ctx.upload_u8(img)
+    ctx.convolute_rgb(out, rgb, f, 224, 224, 3, 2, 32)
+    got = ctx.download_planar(out)
+    assert rel_err(got, want) <= _tol(ctx, mn)
+    # the reference's own calling convention: three separate planes (MobileNet.c:218-246)
+    planes = [ctx.upload_u8(np.ascontiguousarray(img[..., k])) for k in range(3)]
+    out2 = ctx.malloc(n, 32, 112, 112)
+    ctx.convolute(out2, planes[0], planes[1], planes[2], f, 224, 224, 3, 2, 32)
+    assert np.array_equal(ctx.download_planar(out2), got)
+    ctx.set_pad_mode(mn.PAD_REF)
+    ctx.set_input_transform(1.0, 0.0)
+
+
+def test_pool_fc_softmax(ctx, mn, oracle_mod):
+    rng = np.random.default_rng(40)
+    n = 3
+    x = _prep(ctx, mn, oracle_mod, rng.random((n, 1024, 7, 7), dtype=np.float32) * 6)
+    want_pool = oracle_mod.pool(x, rbf16=ctx.dtype == mn.BF16)
+    xin = ctx.upload_planar(x)
+    pooled = ctx.malloc(n, 1024, 1, 1)
+    ctx.pool(pooled, xin, 7, 7, 7, 1024)
+    got_pool = ctx.download_planar(pooled).reshape(n, 1024)
+    assert rel_err(got_pool, want_pool) <= _tol(ctx, mn)
+    w = (rng.standard_normal((1000, 1024)) / 32).astype(np.float32)
+    if ctx.dtype == mn.BF16:
+        w = oracle_mod.round_bf16(w)
+    bias = (rng.standard_normal(1000) * 0.01).astype(np.float32)
+    want_fc = oracle_mod.pointwise(got_pool.reshape(n, 1024, 1, 1), w, 1000, shift=bias, act=oracle_mod.ACT_NONE,
+                                   rbf16=ctx.dtype == mn.BF16).reshape(n, 1000)
+    f = ctx.filter(mn.FC, w, 1024, 1000, None, bias, mn.ACT_NONE)
+    logits = ctx.malloc(n, 1000, 1, 1)
+    ctx.pointwise(logits, pooled, f, 1, 1, 1024, 1000)
+    got_fc = ctx.download_planar(logits).reshape(n, 1000)
+    assert rel_err(got_fc, want_fc) <= _tol(ctx, mn)
+    prob, top1, p1 = ctx.softmax(logits, 1000)
+    oprob, otop1, op1 = oracle_mod.softmax_argmax(got_fc)
+    assert np.array_equal(top1, otop1)
+    assert np.allclose(prob, oprob, rtol=1e-4, atol=1e-7)
+    assert np.allclose(p1, op1, rtol=1e-4)
+
+
+# --------------------------------------------------------------------------- whole network
+def _net_ctx(mn, dtype, synth_net):
+    w, sc, sh = synth_net
+    c = mn.Context(0, dtype)
+    c.set_pad_mode(mn.PAD_TFSAME)
+    c.set_input_transform(1 / 127.5, -1.0)
+    c.set_weights(w, sc, sh, mn.ACT_RELU6)
+    return c
+
+
+def test_fp32_network_per_layer(mn, oracle_mod, synth_net):
+    """BASELINE configs 1-3: layers 1-5, 1-13, full net at N=1, fp32, <= 1e-4 per layer, same top-1."""
+    from mnv1_b200 import synth
+    w, sc, sh = synth_net
+    img = synth.images(1)
+    logits, taps = oracle_mod.forward(img, w, sc, sh, taps=range(1, 29))
+    c = _net_ctx(mn, mn.F32, synth_net)
+    worst = {}
+    for k in list(range(1, 29)):
+        got = c.forward_upto(img, k)
+        worst[k] = rel_err(got.reshape(taps[k].shape), taps[k])
+        assert worst[k] <= FP32_TOL, f"layer {k}: {worst[k]}"
+    got_logits, top1, p1 = c.forward(img)
+    assert rel_err(got_logits, logits) <= FP32_TOL
+    _, otop1, op1 = oracle_mod.softmax_argmax(logits)
+    assert np.array_equal(top1, otop1)
+    assert abs(p1[0] - op1[0]) <= 1e-4 * op1[0] + 1e-7
+    c.close()
+
+
+def test_bf16_network(mn, oracle_mod, synth_net):
+    """bf16 activations / pointwise+FC weights, fp32 accumulate.  Oracle run in the same
+    storage precision (bf16-rounded pointwise/FC weights, outputs rounded per layer).
+    Stated tolerance for the whole 29-layer chain: logits within 0.05 absolute (logit spread
+    is ~0.8), per-layer taps within 4 bf16 ulp-relative on 99.9% of elements, and identical
+    top-1 wherever the oracle's top-1 margin exceeds 0.1."""
+    from mnv1_b200 import synth
+    from mnv1_b200.layers import LAYERS, POINTWISE, FC
+    w, sc, sh = synth_net
+    wq = w.copy()
+    for L in LAYERS:
+        if L.kind in (POINTWISE, FC):
+            wq[L.w_off:L.w_off + L.w_cnt] = oracle_mod.round_bf16(w[L.w_off:L.w_off + L.w_cnt])
+    n = 4
+    img = synth.images(n)
+    logits, taps = oracle_mod.forward(img, wq, sc, sh, rbf16=1, taps=(1, 2, 3, 5, 13, 27))
+    c = _net_ctx(mn, mn.BF16, synth_net)
+    for k in (1, 2, 3, 5, 13, 27):
+        got = c.forward_upto(img, k)
+        err = np.abs(got - taps[k]) / np.maximum(1.0, np.abs(taps[k]))
+        assert np.quantile(err, 0.999) <= 4 * BF16_TOL, f"layer {k}: q99.9 {np.quantile(err, 0.999)}"
+    got_logits, top1, _ = c.forward(img)
+    assert np.max(np.abs(got_logits - logits)) <= 0.05
+    _, otop1, _ = oracle_mod.softmax_argmax(logits)
+    srt = np.sort(logits, axis=1)
+    margin = srt[:, -1] - srt[:, -2]
+    assert np.array_equal(top1[margin > 0.1], otop1[margin > 0.1])
+    c.close()
+
+
+def test_batch_independence_and_graph(mn, synth_net):
+    """Size-independent properties at batch 256 (BASELINE config 4): every image's logits are
+    bit-identical whether it runs alone, eagerly, or inside a graph-replayed batch of 256."""
+    from mnv1_b200 import synth
+    c = _net_ctx(mn, mn.BF16, synth_net)
+    img = synth.images(256)
+    lg, top1, _ = c.forward(img)
+    lg2, top1b, _ = c.forward(img)  # graph replay
+    assert np.array_equal(lg, lg2) and np.array_equal(top1, top1b)
+    for i in (0, 100, 255):
+        l1, t1, _ = c.forward(img[i:i + 1])
+        assert np.array_equal(l1[0], lg[i])
+        assert t1[0] == top1[i]
+    c.use_graph(False)
+    lg3, _, _ = c.forward(img[:7])
+    assert np.array_equal(lg3, lg[:7])
+    assert np.isfinite(lg).all()
+    c.close()
+
+
+def test_synth_images_device_matches_numpy(mn):
+    import torch
+    from mnv1_b200 import synth
+    c = mn.Context(0, mn.BF16)
+    buf = torch.empty(3 * 224 * 224 * 3, dtype=torch.uint8, device="cuda")
+    c.synth_images_device(buf.data_ptr(), 3, 5, synth.IMAGE_SEED)
+    c.sync()
+    assert np.array_equal(buf.cpu().numpy().reshape(3, 224, 224, 3), synth.images(3, first=5))
+    c.close()
+
+
+# --------------------------------------------------------------------------- edges / errors
+def test_errors_and_empty(mn):
+    c = mn.Context(0, mn.BF16)
+    f = c.filter(mn.DEPTHWISE, np.zeros((8, 3, 3), np.float32), 8, 8)
+    a = c.malloc(0, 8, 4, 4)
+    b = c.malloc(0, 8, 4, 4)
+    c.depthwise(b, a, f, 4, 4, 3, 1, 8)  # empty batch is a no-op
+    x = c.malloc(1, 8, 4, 4)
+    y = c.malloc(1, 8, 3, 3)
+    with pytest.raises(mn.Mnv1Error) as e:
+        c.depthwise(y, x, f, 4, 4, 3, 1, 8)  # wrong output shape
+    assert e.value.code == -1
+    with pytest.raises(mn.Mnv1Error) as e:
+        c.depthwise(x, x, f, 4, 4, 5, 1, 8)  # 5x5 not implemented
+    assert e.value.code == -6
+    with pytest.raises(mn.Mnv1Error) as e:
+        c.forward(np.zeros((1, 224, 224, 3), np.uint8))  # no weights
+    assert e.value.code == -5
+    c.close()
