@@ -325,6 +325,13 @@ int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, i
       dev.resize((size_t)9 * cout);
       for (int c = 0; c < cout; ++c)
         for (int t = 0; t < 9; ++t) dev[(size_t)t * cout + c] = w[(size_t)c * 9 + t];
+      if (ctx->dtype == MNV1_BF16) {  // taps with the folded-BN scale multiplied in (depthwise_tma.cu)
+        std::vector<float> sc(dev);
+        if (scale)
+          for (int c = 0; c < cout; ++c)
+            for (int t = 0; t < 9; ++t) sc[(size_t)t * cout + c] *= scale[c];
+        if ((rc = upload_vec(ctx, sc, &f->w_scaled)) != MNV1_OK) return rc;
+      }
       break;
     }
     case MNV1_POINTWISE:
@@ -355,7 +362,7 @@ int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, i
 int mnv1_filter_destroy(mnv1_ctx* ctx, mnv1_filter* f) {
   if (!f) return MNV1_OK;
   if (ctx) cudaStreamSynchronize(ctx->stream);
-  cudaFree(f->w_f32); cudaFree(f->w_bf16); cudaFree(f->scale); cudaFree(f->shift);
+  cudaFree(f->w_f32); cudaFree(f->w_scaled); cudaFree(f->w_bf16); cudaFree(f->scale); cudaFree(f->shift);
   delete f;
   return MNV1_OK;
 }
@@ -371,7 +378,15 @@ static cudaError_t run_stem(mnv1_ctx* ctx, void* out, const uint8_t* r, const ui
 }
 static cudaError_t run_depthwise(mnv1_ctx* ctx, void* out, const void* in, const mnv1_filter* f, int n, int rows,
                                  int cols, int stride) {
-  ctx->launches++; ctx->last_kernel = "depthwise_kernel";
+  ctx->launches++;
+  if (ctx->dtype == MNV1_BF16 && f->w_scaled) {
+    ctx->err.clear();
+    cudaError_t e = mnv1::launch_depthwise_tma((bf16*)out, (const bf16*)in, f->w_scaled, f->shift, (int)f->act, n, rows,
+                                               cols, stride, f->cout, pad_lo_for(ctx, stride), ctx->num_sms,
+                                               ctx->stream, &ctx->err);
+    if (e != cudaErrorNotSupported) { ctx->last_kernel = "depthwise_tma_kernel"; return e; }
+  }
+  ctx->last_kernel = "depthwise_kernel";
   return mnv1::launch_depthwise(ctx->dtype, out, in, f->w_f32, n, rows, cols, stride, f->cout,
                                 pad_lo_for(ctx, stride), Epilogue{f->scale, f->shift, (int)f->act}, ctx->stream);
 }

@@ -25,6 +25,7 @@ struct mnv1_filter {
   int cin = 0, cout = 0;
   mnv1_act act = MNV1_ACT_NONE;
   float* w_f32 = nullptr;   // kernel-native fp32 copy (stem [27][Cout], dw [9][C], pw/fc [Cout][Cin])
+  float* w_scaled = nullptr; // depthwise: [9][C] taps pre-multiplied by `scale` (TMA path)
   bf16* w_bf16 = nullptr;   // bf16 [Cout][Cin] (pointwise / fc, bf16 contexts)
   float* scale = nullptr;   // [Cout] or nullptr
   float* shift = nullptr;   // [Cout] or nullptr
@@ -75,6 +76,10 @@ cudaError_t launch_stem(mnv1_dtype dt, void* out, const StemArgs& a, const float
 cudaError_t launch_depthwise(mnv1_dtype dt, void* out, const void* in, const float* w9xC, int n,
                              int rows, int cols, int stride, int c, int pad_lo, Epilogue ep,
                              cudaStream_t st);
+// TMA-staged depthwise (bf16); cudaErrorNotSupported = no variant for this shape, nothing launched
+cudaError_t launch_depthwise_tma(bf16* out, const bf16* in, const float* w9xC_scaled, const float* shift, int act,
+                                 int n, int rows, int cols, int stride, int c, int pad_lo, int num_sms,
+                                 cudaStream_t st, std::string* err);
 // generic SIMT 1x1 conv / FC: out[M][Cout] = in[M][K] * w[Cout][K]^T  (fp32 contexts, FC)
 cudaError_t launch_pointwise_simt(mnv1_dtype dt, void* out, const void* in, const float* w_f32,
                                   const bf16* w_bf16, long m, int k, int cout, Epilogue ep,
