@@ -350,7 +350,7 @@ int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, i
     cudaError_t e = cudaMalloc(&f->w_bf16, h.size() * 2);
     if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "cudaMalloc(filter bf16) failed");
     CK(ctx, cudaMemcpy(f->w_bf16, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
-    if (kind == MNV1_POINTWISE && cout % 32 == 0 && cin % 8 == 0 && cout <= 1024) {
+    if (kind == MNV1_POINTWISE && cout % 64 == 0 && cin % 8 == 0 && cout <= 1024) {
       std::string err;
       cudaError_t te = mnv1::make_weight_tmap(f.get(), &err);
       if (te != cudaSuccess) return fail(ctx, MNV1_ECUDA, "TMA descriptor for pointwise filter: " + err);

@@ -11,10 +11,9 @@
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32
 //               accumulators in TMEM, two accumulator stages so the epilogue of tile i overlaps
 //               the MMAs of tile i+1)
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> scale/shift/ReLU6 -> bf16 -> 16-byte
-//               global stores of each thread's output row
-// K tails (K = 32 < 64) and M tails are zero-filled by TMA out-of-bounds handling; stores are
-// masked by row.
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> scale/shift/ReLU6 -> bf16 -> 128B-swizzled
+//               shared-memory staging (two 128 x 64 buffers) -> TMA store (cp.async.bulk.tensor)
+// K tails (K = 32 < 64) and M tails are zero-filled on load / clipped on store by the TMA unit.
 #include "common.cuh"
 
 #include <cstdio>
@@ -123,18 +122,20 @@ struct __align__(8) TcBarriers {
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    bf16* __restrict__ out, const float* __restrict__ scale, const float* __restrict__ shift,
-                    int act, long M, int K, int Cout, int stages) {
+                    const __grid_constant__ CUtensorMap tmap_out, const float* __restrict__ scale,
+                    const float* __restrict__ shift, int act, long M, int K, int Cout, int stages) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t OUT_BYTES = TC_BM * 128;       // one 128 x 64 bf16 output block
   constexpr uint32_t TMEM_COLS = 2 * BN;            // two accumulator stages (power of two >= 32)
   static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "tmem cols");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A | B)] 1024-aligned, then scale/shift, then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_scale = reinterpret_cast<float*>(smem + (size_t)stages * STAGE_BYTES);
+  uint8_t* s_out = smem + (size_t)stages * STAGE_BYTES;            // 2 x (128 rows x 128 B), 1024-aligned
+  float* s_scale = reinterpret_cast<float*>(s_out + 2 * OUT_BYTES);
   float* s_shift = s_scale + TC_MAX_COUT;
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(s_shift + TC_MAX_COUT);
 
@@ -151,6 +152,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
     for (int s = 0; s < stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -197,10 +199,12 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
           const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+          const int krem = K - kb * TC_BK;                // K tail: skip the zero-filled 16-wide slices
+          const int nk = krem >= TC_BK ? TC_BK / TC_UMMA_K : (krem + TC_UMMA_K - 1) / TC_UMMA_K;
 #pragma unroll
           for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
             // advance 16 elements = 32 bytes inside the 128B swizzle row: +2 in the (>>4) address field
-            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            if (k < nk) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
           }
           umma_commit(&bars->empty[stage]);              // frees the smem slot when these MMAs retire
           if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -212,36 +216,50 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ================= epilogue warps 2..5 =================
     const int quarter = warp & 3;                        // TMEM lanes 32*quarter .. +31 belong to this warp
+    const int row = quarter * 32 + lane;                 // row of the tile this thread owns
+    const bool leader = threadIdx.x == 64;               // issues the TMA stores
     int as = 0; uint32_t aphase = 0;
+    uint32_t blk = 0;                                    // running 64-column block counter -> staging buffer
     for (long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const long m_idx = (t / n_tiles) * TC_BM;
+      const int m_idx = (int)(t / n_tiles) * TC_BM;
       const int n_idx = (int)(t % n_tiles) * BN;
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
-      const long row = m_idx + quarter * 32 + lane;
-      bf16* orow = out + row * Cout + n_idx;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        uint32_t packed[16];
+      for (int c0 = 0; c0 < BN; c0 += 64, ++blk) {
+        uint8_t* sbuf = s_out + (blk & 1u) * OUT_BYTES;
+        // the store issued two blocks ago read this buffer: wait until it has been consumed
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[n_idx + c0 + j]);
-          const float4 t4 = *reinterpret_cast<const float4*>(&s_shift[n_idx + c0 + j]);
-          const float y0 = apply_epilogue(__uint_as_float(v[j + 0]), s4.x, t4.x, act);
-          const float y1 = apply_epilogue(__uint_as_float(v[j + 1]), s4.y, t4.y, act);
-          const float y2 = apply_epilogue(__uint_as_float(v[j + 2]), s4.z, t4.z, act);
-          const float y3 = apply_epilogue(__uint_as_float(v[j + 3]), s4.w, t4.w, act);
-          packed[j / 2] = pack_bf16x2(y0, y1);
-          packed[j / 2 + 1] = pack_bf16x2(y2, y3);
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)(c0 + 32 * h), v);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 8; e += 4) {
+              const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[n_idx + c0 + 32 * h + j + e]);
+              const float4 t4 = *reinterpret_cast<const float4*>(&s_shift[n_idx + c0 + 32 * h + j + e]);
+              pk[e / 2] = pack_bf16x2(apply_epilogue(__uint_as_float(v[j + e + 0]), s4.x, t4.x, act),
+                                      apply_epilogue(__uint_as_float(v[j + e + 1]), s4.y, t4.y, act));
+              pk[e / 2 + 1] = pack_bf16x2(apply_epilogue(__uint_as_float(v[j + e + 2]), s4.z, t4.z, act),
+                                          apply_epilogue(__uint_as_float(v[j + e + 3]), s4.w, t4.w, act));
+            }
+            // 16-byte chunk index inside the 128-byte row, XOR-swizzled with the row (SWIZZLE_128B)
+            const int chunk = (32 * h + j) / 8;
+            *reinterpret_cast<uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
         }
-        if (row < M) {
-          uint4* o4 = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            o4[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (leader) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_out),
+                       "r"(smem_u32(sbuf)), "r"(n_idx + c0), "r"(m_idx)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();
@@ -249,6 +267,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -277,7 +296,8 @@ EncodeTiledFn get_encode_fn(std::string* err) {
   return fn;
 }
 
-// 2-D bf16 tensor [rows][k] (k contiguous) with a (64 x box_rows) box and 128B swizzle.
+// 2-D bf16 tensor [rows][k] (k contiguous) with a (64 x box_rows) box and 128B swizzle
+// (used for A = activations, B = filter and the output tile alike).
 cudaError_t encode_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t k, uint32_t box_rows,
                       std::string* err) {
   EncodeTiledFn fn = get_encode_fn(err);
@@ -305,16 +325,16 @@ int pick_bn(int cout) {
   if (cout % 256 == 0) return 256;
   if (cout % 128 == 0) return 128;
   if (cout % 64 == 0) return 64;
-  if (cout % 32 == 0) return 32;
   return 0;
 }
 
 template <int BN>
-cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, const float* scale,
+cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const float* scale,
                       const float* shift, int act, long m, int k, int cout, int num_sms, cudaStream_t st) {
   const int num_kb = (k + TC_BK - 1) / TC_BK;
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2;
-  const size_t fixed = 1024 /*align slack*/ + 2 * TC_MAX_COUT * sizeof(float) + sizeof(TcBarriers);
+  const size_t fixed = 1024 /*align slack*/ + 2 * TC_BM * 128 /*output staging*/ + 2 * TC_MAX_COUT * sizeof(float) +
+                       sizeof(TcBarriers);
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   // a ring deeper than ~2 tiles' worth of k-blocks only costs smem; keep at least 2
@@ -331,7 +351,7 @@ cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, c
   }
   const long tiles = ((m + TC_BM - 1) / TC_BM) * (cout / BN);
   const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-  pointwise_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(ta, tb, out, scale, shift, act, m, k, cout, stages);
+  pointwise_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(ta, tb, to, scale, shift, act, m, k, cout, stages);
   return cudaGetLastError();
 }
 
@@ -340,7 +360,7 @@ cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, bf16* out, c
 cudaError_t make_weight_tmap(mnv1_filter* f, std::string* err) {
   const int bn = pick_bn(f->cout);
   if (!bn || f->cin % 8 || f->cout > TC_MAX_COUT) {
-    if (err) *err = "pointwise tcgen05 path needs Cout % 32 == 0, Cout <= 1024 and Cin % 8 == 0";
+    if (err) *err = "pointwise tcgen05 path needs Cout % 64 == 0, Cout <= 1024 and Cin % 8 == 0";
     return cudaErrorInvalidValue;
   }
   cudaError_t e = encode_2d(&f->tmap_b, f->w_bf16, (uint64_t)f->cout, (uint64_t)f->cin, (uint32_t)bn, err);
@@ -355,14 +375,15 @@ cudaError_t launch_pointwise_tc(bf16* out, const bf16* in, const mnv1_filter* f,
     return cudaErrorInvalidValue;
   }
   if (m <= 0) return cudaSuccess;
-  CUtensorMap ta;
+  CUtensorMap ta, to;
   cudaError_t e = encode_2d(&ta, in, (uint64_t)m, (uint64_t)k, TC_BM, err);
   if (e != cudaSuccess) return e;
+  e = encode_2d(&to, out, (uint64_t)m, (uint64_t)cout, TC_BM, err);
+  if (e != cudaSuccess) return e;
   switch (f->tmap_bn) {
-    case 256: return launch_bn<256>(ta, f->tmap_b, out, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
-    case 128: return launch_bn<128>(ta, f->tmap_b, out, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
-    case 64:  return launch_bn<64>(ta, f->tmap_b, out, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
-    case 32:  return launch_bn<32>(ta, f->tmap_b, out, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
+    case 256: return launch_bn<256>(ta, f->tmap_b, to, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
+    case 128: return launch_bn<128>(ta, f->tmap_b, to, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
+    case 64:  return launch_bn<64>(ta, f->tmap_b, to, f->scale, f->shift, f->act, m, k, cout, num_sms, st);
   }
   return cudaErrorInvalidValue;
 }
