@@ -12,37 +12,45 @@ namespace mnv1 {
 cudaError_t launch_fc_f32in(float* out, const float* in, const float* w_f32, const bf16* w_bf16, long m, int k,
                             int cout, Epilogue ep, cudaStream_t st);
 
-// in: NHWC [n][hw][c]; one thread per (image, channel pair/quad); lanes walk channels.
+// in: NHWC [n][hw][c].  A CTA reduces 256 channels of one image: 64 channel quads x 4 pixel
+// phases (pixels p = phase, phase+4, ...) so the 49 row reads of a quad are spread over 4 threads
+// with independent loads in flight, then a shared-memory fold of the 4 partial sums.
 template <typename T, typename TO>
 __global__ void __launch_bounds__(256) pool_kernel(TO* __restrict__ out, const T* __restrict__ in, int n, int hw,
                                                    int c) {
-  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int cq = c / 4;
-  if (idx >= (long)n * cq) return;
-  const int img = (int)(idx / cq), c0 = (int)(idx % cq) * 4;
-  const T* p = in + (long)img * hw * c + c0;
+  __shared__ float part[4][64][4];
+  const int img = blockIdx.x, q = threadIdx.x & 63, ph = threadIdx.x >> 6;
+  const int c0 = blockIdx.y * 256 + q * 4;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  for (int i = 0; i < hw; ++i) {
-    if constexpr (sizeof(T) == 2) {
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (long)i * c));
-      s0 += bf16lo_to_f32(v.x); s1 += bf16hi_to_f32(v.x); s2 += bf16lo_to_f32(v.y); s3 += bf16hi_to_f32(v.y);
-    } else {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(p + (long)i * c));
-      s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+  if (c0 < c) {
+    const T* p = in + (long)img * hw * c + c0;
+#pragma unroll 4
+    for (int i = ph; i < hw; i += 4) {
+      if constexpr (sizeof(T) == 2) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (long)i * c));
+        s0 += bf16lo_to_f32(v.x); s1 += bf16hi_to_f32(v.x); s2 += bf16lo_to_f32(v.y); s3 += bf16hi_to_f32(v.y);
+      } else {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + (long)i * c));
+        s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+      }
     }
   }
-  const float inv = 1.0f / (float)hw;
-  TO* o = out + (long)img * c + c0;
-  o[0] = from_f32<TO>(s0 * inv); o[1] = from_f32<TO>(s1 * inv);
-  o[2] = from_f32<TO>(s2 * inv); o[3] = from_f32<TO>(s3 * inv);
+  part[ph][q][0] = s0; part[ph][q][1] = s1; part[ph][q][2] = s2; part[ph][q][3] = s3;
+  __syncthreads();
+  if (ph == 0 && c0 < c) {
+    const float inv = 1.0f / (float)hw;
+    TO* o = out + (long)img * c + c0;
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      o[v] = from_f32<TO>((part[0][q][v] + part[1][q][v] + part[2][q][v] + part[3][q][v]) * inv);
+  }
 }
 
 cudaError_t launch_pool(mnv1_dtype dt, void* out, const void* in, int n, int hw, int c, bool out_f32,
                         cudaStream_t st) {
   if (c % 4) return cudaErrorInvalidValue;
   if (n <= 0) return cudaSuccess;
-  const long total = (long)n * (c / 4);
-  const unsigned grid = (unsigned)((total + 255) / 256);
+  dim3 grid(n, (c + 255) / 256);
   if (dt == MNV1_F32) pool_kernel<float, float><<<grid, 256, 0, st>>>((float*)out, (const float*)in, n, hw, c);
   else if (out_f32)   pool_kernel<bf16, float><<<grid, 256, 0, st>>>((float*)out, (const bf16*)in, n, hw, c);
   else                pool_kernel<bf16, bf16><<<grid, 256, 0, st>>>((bf16*)out, (const bf16*)in, n, hw, c);

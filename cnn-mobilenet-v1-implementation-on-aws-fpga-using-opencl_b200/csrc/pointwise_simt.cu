@@ -25,16 +25,25 @@ __global__ void __launch_bounds__(256) pointwise_simt_kernel(TO* __restrict__ ou
   float acc[4][4] = {};
   // loader mapping: 256 threads fetch a 64 x 16 slice, k fastest (contiguous in memory)
   const int lr = tid / 4, lk = (tid % 4) * 4;
-  for (int k0 = 0; k0 < K; k0 += PS_BK) {
+  // register-prefetched k loop: the global loads of slice k0+BK are in flight while slice k0 is
+  // multiplied out of shared memory
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int k = k0 + lk + q;
       const long m = m0 + lr;
-      sA[lk + q][lr] = (m < M && k < K) ? to_f32<TA>(in[m * K + k]) : 0.f;
+      ra[q] = (m < M && k < K) ? to_f32<TA>(in[m * K + k]) : 0.f;
       const int co = n0 + lr;
-      sB[lk + q][lr] = (co < Cout && k < K) ? to_f32<TW>(w[(long)co * K + k]) : 0.f;
+      rb[q] = (co < Cout && k < K) ? to_f32<TW>(w[(long)co * K + k]) : 0.f;
     }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += PS_BK) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { sA[lk + q][lr] = ra[q]; sB[lk + q][lr] = rb[q]; }
     __syncthreads();
+    if (k0 + PS_BK < K) fetch(k0 + PS_BK);
 #pragma unroll
     for (int kk = 0; kk < PS_BK; ++kk) {
       const float4 a = *reinterpret_cast<const float4*>(&sA[kk][tm]);

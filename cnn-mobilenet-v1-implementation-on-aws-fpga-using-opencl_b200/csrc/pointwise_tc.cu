@@ -5,14 +5,18 @@
 // The NHWC feature map IS the K-major A operand and the reference's [Cout][Cin] filter order
 // (kernel.cl:106) IS the K-major B operand, so neither is re-laid out.
 //
-// Persistent, warp-specialised CTA (one per SM), 192 threads:
+// Persistent, warp-specialised CTA (one per SM), 320 threads:
 //   warp 0      TMA producer: A tile 128 x 64 and B tile BN x 64 (bf16, 128B swizzle) per k-block
 //               into a ring of `stages` shared-memory slots (full/empty mbarriers)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp32
 //               accumulators in TMEM, two accumulator stages so the epilogue of tile i overlaps
 //               the MMAs of tile i+1)
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> scale/shift/ReLU6 -> bf16 -> 128B-swizzled
-//               shared-memory staging (two 128 x 64 buffers) -> TMA store (cp.async.bulk.tensor)
+//   warps 2-9   epilogue (two warps per TMEM lane quarter, each taking 32 of a 64-column block):
+//               tcgen05.ld 32 lanes x 32 columns -> fma(scale, shift) -> ReLU folded into the bf16
+//               convert, 6-cap as min.bf16x2 -> 128B-swizzled shared-memory staging (two 128 x 64
+//               buffers) -> TMA store (cp.async.bulk.tensor).  With one warp per scheduler and
+//               ~10 instructions per element the epilogue, not the MMAs, set the pace
+//               (profiles/r01_pw_v1_ncu.txt); it is now ~3 instructions per element on 8 warps.
 // K tails (K = 32 < 64) and M tails are zero-filled on load / clipped on store by the TMA unit.
 #include "common.cuh"
 
@@ -25,7 +29,8 @@ namespace {
 constexpr int TC_BM = 128;       // UMMA M (cta_group::1)
 constexpr int TC_BK = 64;        // bf16 elements per k-block = 128 bytes = one swizzle row
 constexpr int TC_UMMA_K = 16;    // K per tcgen05.mma for 16-bit inputs
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_COUT = 1024;
 
@@ -47,12 +52,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(20000u)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
@@ -110,31 +115,57 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// fp32 pair -> bf16x2; ReLU rides on the convert, the upper cap is a packed min (exact: rounding is
+// monotonic and the cap is representable)
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, uint32_t cap2) {
+  uint32_t d;
+  if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  asm("min.bf16x2 %0, %0, %1;" : "+r"(d) : "r"(cap2));
+  return d;
+}
+
 struct __align__(8) TcBarriers {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t resb_full;
   uint32_t tmem_base;
   uint32_t pad;
 };
 
-template <int BN>
+// BN: UMMA N; RELU: activation folded into the convert; RESB: the whole filter (all k-blocks of the
+// single n-tile) stays resident in shared memory for the life of the CTA and the ring carries A only.
+template <int BN, bool RELU, bool RESB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const float* __restrict__ scale,
-                    const float* __restrict__ shift, int act, long M, int K, int Cout, int stages) {
+                    const float* __restrict__ shift, uint32_t cap2, long M, int K, int Cout, int stages, int group) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
-  constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t STAGE_BYTES = A_BYTES + (RESB ? 0u : B_BYTES);
   constexpr uint32_t OUT_BYTES = TC_BM * 128;       // one 128 x 64 bf16 output block
-  constexpr uint32_t TMEM_COLS = 2 * BN;            // two accumulator stages (power of two >= 32)
-  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "tmem cols");
+  // two accumulator stages of 256 fp32 columns each; a stage holds `group` = 256/BN consecutive
+  // m-tiles when the layer has a single n-tile, so one full/empty handshake covers 256 columns
+  constexpr uint32_t ACC_COLS = 256;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A | B)] 1024-aligned, then scale/shift, then barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_out = smem + (size_t)stages * STAGE_BYTES;            // 2 x (128 rows x 128 B), 1024-aligned
+  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  uint8_t* s_resb = smem + (size_t)stages * STAGE_BYTES;           // resident filter (RESB): num_kb x B tile
+  uint8_t* s_out = s_resb + (RESB ? (size_t)num_kb * B_BYTES : 0);  // 2 x (128 rows x 128 B), 1024-aligned
   float* s_scale = reinterpret_cast<float*>(s_out + 2 * OUT_BYTES);
   float* s_shift = s_scale + TC_MAX_COUT;
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(s_shift + TC_MAX_COUT);
@@ -142,8 +173,9 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = Cout / BN;
   const long m_tiles = (M + TC_BM - 1) / TC_BM;
-  const long num_tiles = m_tiles * n_tiles;
-  const int num_kb = (K + TC_BK - 1) / TC_BK;
+  // work unit = `group` consecutive m-tiles of one n-tile (group > 1 only when n_tiles == 1)
+  const long m_groups = (m_tiles + group - 1) / group;
+  const long num_units = m_groups * n_tiles;
 
   for (int i = threadIdx.x; i < Cout; i += TC_THREADS) {
     s_scale[i] = scale ? scale[i] : 1.f;
@@ -154,7 +186,8 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
     for (int s = 0; s < stages; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], TC_EPI_WARPS); }
+    mbar_init(&bars->resb_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -171,16 +204,24 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
+      if (RESB) {  // the filter is loaded once: every k-block of the single n-tile
+        mbar_expect_tx(&bars->resb_full, (uint32_t)num_kb * B_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(s_resb + (size_t)kb * B_BYTES, &tmap_b, &bars->resb_full, kb * TC_BK, 0);
+      }
       int stage = 0; uint32_t phase = 0;
-      for (long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_idx = (int)(t / n_tiles) * TC_BM, n_idx = (int)(t % n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&bars->empty[stage], phase ^ 1u);
-          uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
-          mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &bars->full[stage], kb * TC_BK, m_idx);
-          tma_load_2d(sa + A_BYTES, &tmap_b, &bars->full[stage], kb * TC_BK, n_idx);
-          if (++stage == stages) { stage = 0; phase ^= 1u; }
+      for (long u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const long mt0 = (u / n_tiles) * group;
+        const int n_idx = (int)(u % n_tiles) * BN;
+        for (int g = 0; g < group && mt0 + g < m_tiles; ++g) {
+          const int m_idx = (int)(mt0 + g) * TC_BM;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&bars->empty[stage], phase ^ 1u);
+            uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+            mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, &bars->full[stage], kb * TC_BK, m_idx);
+            if (!RESB) tma_load_2d(sa + A_BYTES, &tmap_b, &bars->full[stage], kb * TC_BK, n_idx);
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -190,74 +231,83 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       constexpr uint32_t idesc = make_idesc(BN);
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      for (long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);   // epilogue has drained this accumulator
+      if (RESB) { mbar_wait(&bars->resb_full, 0); tc_fence_after(); }
+      const uint32_t resb_u = smem_u32(s_resb);
+      for (long u = blockIdx.x; u < num_units; u += gridDim.x) {
+        const long mt0 = (u / n_tiles) * group;
+        mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&bars->full[stage], phase);          // TMA bytes have landed
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
-          const int krem = K - kb * TC_BK;                // K tail: skip the zero-filled 16-wide slices
-          const int nk = krem >= TC_BK ? TC_BK / TC_UMMA_K : (krem + TC_UMMA_K - 1) / TC_UMMA_K;
+        for (int g = 0; g < group && mt0 + g < m_tiles; ++g) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)as * ACC_COLS + (uint32_t)(g * BN);
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&bars->full[stage], phase);          // TMA bytes have landed
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+            const uint64_t da = make_smem_desc(sa);
+            const uint64_t db = make_smem_desc(RESB ? resb_u + (uint32_t)kb * B_BYTES : sa + A_BYTES);
+            const int krem = K - kb * TC_BK;                // K tail: skip the zero-filled 16-wide slices
+            const int nk = krem >= TC_BK ? TC_BK / TC_UMMA_K : (krem + TC_UMMA_K - 1) / TC_UMMA_K;
 #pragma unroll
-          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-            // advance 16 elements = 32 bytes inside the 128B swizzle row: +2 in the (>>4) address field
-            if (k < nk) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+              // advance 16 elements = 32 bytes inside the 128B swizzle row: +2 in the (>>4) address field
+              if (k < nk) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(&bars->empty[stage]);              // frees the smem slot when these MMAs retire
+            if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(&bars->empty[stage]);              // frees the smem slot when these MMAs retire
-          if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&bars->tmem_full[as]);               // accumulator complete -> epilogue
+        umma_commit(&bars->tmem_full[as]);                 // accumulator stage complete -> epilogue
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
   } else {
-    // ================= epilogue warps 2..5 =================
+    // ================= epilogue warps 2..9 =================
     const int quarter = warp & 3;                        // TMEM lanes 32*quarter .. +31 belong to this warp
+    const int half = (warp - 2) >> 2;                    // which 32 columns of each 64-column block
     const int row = quarter * 32 + lane;                 // row of the tile this thread owns
     const bool leader = threadIdx.x == 64;               // issues the TMA stores
+    const uint32_t s_out_u = smem_u32(s_out);
+    const uint32_t s_scale_u = smem_u32(s_scale), s_shift_u = smem_u32(s_shift);
+    const uint32_t row_off = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);
     int as = 0; uint32_t aphase = 0;
     uint32_t blk = 0;                                    // running 64-column block counter -> staging buffer
-    for (long t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m_idx = (int)(t / n_tiles) * TC_BM;
-      const int n_idx = (int)(t % n_tiles) * BN;
+    for (long u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const long mt0 = (u / n_tiles) * group;
+      const int n_idx = (int)(u % n_tiles) * BN;
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * ACC_COLS + (uint32_t)(32 * half);
+      const int nblk = group * (BN / 64);                // 64-column blocks in this accumulator stage
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 64, ++blk) {
-        uint8_t* sbuf = s_out + (blk & 1u) * OUT_BYTES;
+      for (int b = 0; b < nblk; ++b) {
+        const int g = b / (BN / 64), c0 = (b % (BN / 64)) * 64;
+        if (mt0 + g >= m_tiles) break;                   // uniform: the last group may be short
+        const int m_idx = (int)(mt0 + g) * TC_BM;
+        const uint32_t sbuf = s_out_u + (blk & 1u) * OUT_BYTES;
+        ++blk;
         // the store issued two blocks ago read this buffer: wait until it has been consumed
         if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(b * 64), v);
+        const uint32_t col = (uint32_t)(n_idx + c0 + 32 * half);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld32(taddr + (uint32_t)(c0 + 32 * h), v);
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 8; e += 4) {
-              const float4 s4 = *reinterpret_cast<const float4*>(&s_scale[n_idx + c0 + 32 * h + j + e]);
-              const float4 t4 = *reinterpret_cast<const float4*>(&s_shift[n_idx + c0 + 32 * h + j + e]);
-              pk[e / 2] = pack_bf16x2(apply_epilogue(__uint_as_float(v[j + e + 0]), s4.x, t4.x, act),
-                                      apply_epilogue(__uint_as_float(v[j + e + 1]), s4.y, t4.y, act));
-              pk[e / 2 + 1] = pack_bf16x2(apply_epilogue(__uint_as_float(v[j + e + 2]), s4.z, t4.z, act),
-                                          apply_epilogue(__uint_as_float(v[j + e + 3]), s4.w, t4.w, act));
-            }
-            // 16-byte chunk index inside the 128-byte row, XOR-swizzled with the row (SWIZZLE_128B)
-            const int chunk = (32 * h + j) / 8;
-            *reinterpret_cast<uint4*>(sbuf + row * 128 + ((chunk ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
+        for (int j = 0; j < 32; j += 8) {
+          const float4 s0 = lds128f(s_scale_u + (col + j) * 4u), s1 = lds128f(s_scale_u + (col + j + 4) * 4u);
+          const float4 t0 = lds128f(s_shift_u + (col + j) * 4u), t1 = lds128f(s_shift_u + (col + j + 4) * 4u);
+          const uint32_t p0 = pack2<RELU>(fmaf(__uint_as_float(v[j + 0]), s0.x, t0.x), fmaf(__uint_as_float(v[j + 1]), s0.y, t0.y), cap2);
+          const uint32_t p1 = pack2<RELU>(fmaf(__uint_as_float(v[j + 2]), s0.z, t0.z), fmaf(__uint_as_float(v[j + 3]), s0.w, t0.w), cap2);
+          const uint32_t p2 = pack2<RELU>(fmaf(__uint_as_float(v[j + 4]), s1.x, t1.x), fmaf(__uint_as_float(v[j + 5]), s1.y, t1.y), cap2);
+          const uint32_t p3 = pack2<RELU>(fmaf(__uint_as_float(v[j + 6]), s1.z, t1.z), fmaf(__uint_as_float(v[j + 7]), s1.w, t1.w), cap2);
+          // 16-byte chunk index inside the 128-byte row, XOR-swizzled with the row (SWIZZLE_128B)
+          const uint32_t chunk = (uint32_t)(4 * half + j / 8);
+          sts128(sbuf + row_off + ((chunk ^ row_x) << 4), p0, p1, p2, p3);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
         if (leader) {
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_out),
-                       "r"(smem_u32(sbuf)), "r"(n_idx + c0), "r"(m_idx)
+                       "r"(sbuf), "r"(n_idx + c0), "r"(m_idx)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -332,26 +382,45 @@ template <int BN>
 cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const float* scale,
                       const float* shift, int act, long m, int k, int cout, int num_sms, cudaStream_t st) {
   const int num_kb = (k + TC_BK - 1) / TC_BK;
-  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (size_t)BN * TC_BK * 2;
-  const size_t fixed = 1024 /*align slack*/ + 2 * TC_BM * 128 /*output staging*/ + 2 * TC_MAX_COUT * sizeof(float) +
-                       sizeof(TcBarriers);
+  const int n_tiles = cout / BN;
+  const size_t b_bytes = (size_t)BN * TC_BK * 2;
+  // resident filter: single n-tile and the whole [BN][K] filter fits in 64 KB
+  const bool resb = n_tiles == 1 && (size_t)num_kb * b_bytes <= 64 * 1024;
+  const int group = n_tiles == 1 ? 256 / BN : 1;
+  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (resb ? 0 : b_bytes);
+  const size_t fixed = 1024 /*align slack*/ + (resb ? (size_t)num_kb * b_bytes : 0) + 2 * TC_BM * 128 /*output staging*/ +
+                       2 * TC_MAX_COUT * sizeof(float) + sizeof(TcBarriers);
   int stages = (int)((227 * 1024 - fixed) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  // a ring deeper than ~2 tiles' worth of k-blocks only costs smem; keep at least 2
+  // a ring deeper than ~2 tiles' worth of k-blocks only costs smem; keep at least 4
   int want = 2 * num_kb < 4 ? 4 : 2 * num_kb;
+  if (resb && want < 8) want = 8;
   if (stages > want) stages = want;
   if (stages < 2) return cudaErrorInvalidValue;
   const size_t smem = fixed + stages * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(pointwise_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024);
+    cudaError_t e = cudaSuccess;
+    auto set = [&](const void* fn) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    };
+    set((const void*)pointwise_tc_kernel<BN, true, true>);
+    set((const void*)pointwise_tc_kernel<BN, true, false>);
+    set((const void*)pointwise_tc_kernel<BN, false, true>);
+    set((const void*)pointwise_tc_kernel<BN, false, false>);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const long tiles = ((m + TC_BM - 1) / TC_BM) * (cout / BN);
-  const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-  pointwise_tc_kernel<BN><<<grid, TC_THREADS, smem, st>>>(ta, tb, to, scale, shift, act, m, k, cout, stages);
+  const long m_tiles = (m + TC_BM - 1) / TC_BM;
+  const long units = ((m_tiles + group - 1) / group) * n_tiles;
+  const unsigned grid = (unsigned)(units < num_sms ? units : num_sms);
+  const uint32_t cap2 = act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;  // bf16x2 (6, 6) or (+inf, +inf)
+  const bool relu = act != MNV1_ACT_NONE;
+#define PW_LAUNCH(R, B) \
+  pointwise_tc_kernel<BN, R, B><<<grid, TC_THREADS, smem, st>>>(ta, tb, to, scale, shift, cap2, m, k, cout, stages, group)
+  if (relu) { if (resb) PW_LAUNCH(true, true); else PW_LAUNCH(true, false); }
+  else      { if (resb) PW_LAUNCH(false, true); else PW_LAUNCH(false, false); }
+#undef PW_LAUNCH
   return cudaGetLastError();
 }
 
