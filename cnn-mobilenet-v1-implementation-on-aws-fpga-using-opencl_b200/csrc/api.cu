@@ -318,6 +318,13 @@ int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, i
       dev.resize((size_t)27 * cout);
       for (int o = 0; o < cout; ++o)
         for (int t = 0; t < 27; ++t) dev[(size_t)t * cout + o] = w[(size_t)o * 27 + t];
+      if (ctx->dtype == MNV1_BF16 && cout == 32) {  // tensor-core stem: prepared lazily per input transform
+        f->h_w.assign(w, w + (size_t)27 * cout);
+        if (scale) f->h_scale.assign(scale, scale + cout);
+        if (shift) f->h_shift.assign(shift, shift + cout);
+        if (cudaMalloc(&f->wq, 32 * 32 * sizeof(__half)) != cudaSuccess || cudaMalloc(&f->shift2, 32 * 4) != cudaSuccess)
+          return fail(ctx, MNV1_ENOMEM, "cudaMalloc(stem filter) failed");
+      }
       break;
     }
     case MNV1_DEPTHWISE: {  // [C][3][3] (kernel.cl:77) -> [9][C]
@@ -362,18 +369,38 @@ int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, i
 int mnv1_filter_destroy(mnv1_ctx* ctx, mnv1_filter* f) {
   if (!f) return MNV1_OK;
   if (ctx) cudaStreamSynchronize(ctx->stream);
-  cudaFree(f->w_f32); cudaFree(f->w_scaled); cudaFree(f->w_bf16); cudaFree(f->scale); cudaFree(f->shift);
+  cudaFree(f->w_f32); cudaFree(f->w_scaled); cudaFree(f->w_bf16); cudaFree(f->wq); cudaFree(f->shift2); cudaFree(f->scale); cudaFree(f->shift);
   delete f;
   return MNV1_OK;
 }
 
 // ---------------------------------------------------------------- raw launches (device pointers)
+// (re)build the stem's fp16 filter bank for the context's current input transform; must run
+// outside graph capture (it copies synchronously)
+static int prepare_stem(mnv1_ctx* ctx, mnv1_filter* f) {
+  if (!f || !f->wq || ctx->in_scale == 0.f) return MNV1_OK;
+  if (f->prepared && f->prep_scale == ctx->in_scale && f->prep_bias == ctx->in_bias) return MNV1_OK;
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  CK(ctx, mnv1::stem_tc_prepare(f->h_w.data(), f->h_scale.empty() ? nullptr : f->h_scale.data(),
+                                f->h_shift.empty() ? nullptr : f->h_shift.data(), ctx->in_scale, ctx->in_bias, f->wq,
+                                f->shift2, &f->p0));
+  f->prep_scale = ctx->in_scale; f->prep_bias = ctx->in_bias; f->prepared = true;
+  return MNV1_OK;
+}
+
 static cudaError_t run_stem(mnv1_ctx* ctx, void* out, const uint8_t* r, const uint8_t* g, const uint8_t* b,
                             int pix_stride, long img_stride, const mnv1_filter* f, int n, int rows, int cols,
                             int stride) {
   mnv1::StemArgs a{r, g, b, pix_stride, img_stride, n, rows, cols, stride, f->cout, pad_lo_for(ctx, stride),
                    ctx->in_scale, ctx->in_bias};
-  ctx->launches++; ctx->last_kernel = "stem_kernel";
+  ctx->launches++;
+  if (ctx->dtype == MNV1_BF16 && f->prepared && f->prep_scale == ctx->in_scale && f->prep_bias == ctx->in_bias) {
+    ctx->err.clear();
+    cudaError_t e = mnv1::launch_stem_tc((bf16*)out, a, f->wq, f->scale, f->shift2, f->p0, (int)f->act, ctx->num_sms,
+                                         ctx->stream, &ctx->err);
+    if (e != cudaErrorNotSupported) { ctx->last_kernel = "stem_tc_kernel"; return e; }
+  }
+  ctx->last_kernel = "stem_kernel";
   return mnv1::launch_stem(ctx->dtype, out, a, f->w_f32, Epilogue{f->scale, f->shift, (int)f->act}, ctx->stream);
 }
 static cudaError_t run_depthwise(mnv1_ctx* ctx, void* out, const void* in, const mnv1_filter* f, int n, int rows,
@@ -424,6 +451,8 @@ static int convolute_common(mnv1_ctx* ctx, mnv1_buf* out, const uint8_t* r, cons
   if (rc) return rc;
   const size_t plane = (size_t)rows * cols * pix_stride;
   if (avail_bytes < plane * out->n) return fail(ctx, MNV1_EINVAL, "convolute: image buffer too small for the batch");
+  rc = prepare_stem(ctx, const_cast<mnv1_filter*>(f));
+  if (rc) return rc;
   TimedLaunch tl(ctx);
   CK(ctx, run_stem(ctx, out->d, r, g, b, pix_stride, (long)plane, f, out->n, rows, cols, stride));
   return MNV1_OK;
@@ -680,7 +709,7 @@ static int check_ready(mnv1_ctx* ctx, int n) {
     int rc = mnv1_plan(ctx, n);
     if (rc) return rc;
   }
-  return MNV1_OK;
+  return prepare_stem(ctx, ctx->net[0]);
 }
 
 int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images, int n, void* d_logits, void* d_top1, void* d_prob) {

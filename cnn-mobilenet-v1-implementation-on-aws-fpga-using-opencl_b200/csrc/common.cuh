@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -29,6 +30,13 @@ struct mnv1_filter {
   bf16* w_bf16 = nullptr;   // bf16 [Cout][Cin] (pointwise / fc, bf16 contexts)
   float* scale = nullptr;   // [Cout] or nullptr
   float* shift = nullptr;   // [Cout] or nullptr
+  // stem on tensor cores (bf16 contexts): fp16 filter bank x input scale and the folded shift are
+  // rebuilt whenever the context's input transform changes (stem_tc.cu)
+  std::vector<float> h_w, h_scale, h_shift;
+  __half* wq = nullptr;
+  float* shift2 = nullptr;
+  float prep_scale = 0.f, prep_bias = 0.f, p0 = 0.f;
+  bool prepared = false;
   CUtensorMap tmap_b;       // TMA descriptor of w_bf16 (pointwise, bf16 contexts)
   bool has_tmap = false;
   int tmap_bn = 0;          // N-tile the descriptor's box was built for
@@ -73,6 +81,11 @@ struct StemArgs {
 };
 cudaError_t launch_stem(mnv1_dtype dt, void* out, const StemArgs& a, const float* w27xC,
                         Epilogue ep, cudaStream_t st);
+cudaError_t stem_tc_prepare(const float* w_oihw_host, const float* scale_host, const float* shift_host,
+                            float in_scale, float in_bias, __half* wq_dev, float* shift2_dev, float* p0_out);
+cudaError_t launch_stem_tc(bf16* out, const StemArgs& a, const __half* wq_dev, const float* scale_dev,
+                           const float* shift2_dev, float p0, int act, int num_sms, cudaStream_t st,
+                           std::string* err);
 cudaError_t launch_depthwise(mnv1_dtype dt, void* out, const void* in, const float* w9xC, int n,
                              int rows, int cols, int stride, int c, int pad_lo, Epilogue ep,
                              cudaStream_t st);

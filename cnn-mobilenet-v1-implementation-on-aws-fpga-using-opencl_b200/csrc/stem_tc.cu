@@ -1,0 +1,359 @@
+// stem_tc.cu — layer 1 (3x3 conv, 3 colour planes -> 32 maps) on tcgen05 for bf16 contexts.
+//
+// Same contract as stem.cu (`convolute`, kernel.cl:2-60): tap order R,G,B planes x row offset x
+// column offset (kernel.cl:15-51), intended semantics.  At 21.7 MFLOP per image the CUDA-core
+// version is FFMA-bound (5.5 GFLOP per 256-image batch vs a 37 us HBM roofline), so the layer
+// runs as an implicit GEMM  D[pixel][32] = A[pixel][27] . B[32][27]^T :
+//   * A: each thread gathers the 27 u8 taps of ONE output pixel and widens them EXACTLY to fp16
+//     (0x6400|b is 1024+b in fp16; one HSUB2 per pair), written as a K-major 128B-swizzled row;
+//   * B: the filter bank times the input scale, rounded to fp16, built once per CTA;
+//   * D: 128 pixels x 32 channels, fp32 in TMEM, two accumulator/A-tile buffers so the gather of
+//     tile i+1 overlaps the MMA + epilogue of tile i;
+//   * epilogue: tcgen05.ld -> fma(scale, shift') -> ReLU on the bf16 convert, 6-cap as
+//     min.bf16x2 -> 64B-swizzled staging -> TMA store of the contiguous 8 KB NHWC tile.
+// The input transform x' = s*x + b is folded:  conv(x') = sum wq*(x - p0), wq = fp16(w*s),
+// p0 = -b/s (127.5 for the Keras preprocessing, exact in fp16); border taps read p0, so the
+// zero padding of x' is exact and the constant -p0*sum(wq) moves into the shift.
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace mnv1 {
+namespace {
+
+constexpr int ST_THREADS = 128;
+constexpr int ST_C = 32;
+constexpr uint32_t ST_A_BYTES = 128 * 128;   // 128 pixels x 128-byte swizzle rows (first 64 B = 32 fp16 used)
+constexpr uint32_t ST_B_BYTES = 32 * 128;
+constexpr uint32_t ST_O_BYTES = 128 * 64;    // 128 pixels x 32 bf16
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "ST_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra ST_DONE;\n"
+      "bra ST_WAIT;\n"
+      "ST_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity), "r"(20000u)
+      : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// K-major, 128B-swizzled operand descriptor (see pointwise_tc.cu)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16, D = f32, A = B = fp16 (format 0), K-major, N = 32, M = 128
+constexpr uint32_t ST_IDESC = (1u << 4) | ((uint32_t)(ST_C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(ST_IDESC), "r"(accumulate)
+      : "memory");
+}
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, uint32_t cap2) {
+  uint32_t d;
+  if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  asm("min.bf16x2 %0, %0, %1;" : "+r"(d) : "r"(cap2));
+  return d;
+}
+// two u8 values (low bytes of a, b) -> exact fp16 pair
+__device__ __forceinline__ uint32_t u8x2_to_f16x2(uint32_t a, uint32_t b) {
+  uint32_t v = __byte_perm(a, b, 0x5410) | 0x64006400u;   // (1024 + a, 1024 + b)
+  __half2 h = __hsub2(*reinterpret_cast<__half2*>(&v), __half2half2(__ushort_as_half((unsigned short)0x6400)));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct StemTcParams {
+  const uint8_t *r, *g, *b;
+  int pix_stride; long img_stride;
+  int n, rows, cols, orows, ocols, pad_lo;
+  const __half* wq;      // [32][32] fp16: wq[o][k] = fp16(w[o][k] * in_scale), k >= 27 zero
+  const float* scale;    // [32] or nullptr
+  const float* shift2;   // [32] shift + scale * (-p0 * sum_k wq[o][k])
+  uint32_t cap2;
+  uint32_t pad_f16x2;    // fp16(p0) in both halves
+  long m_total;
+};
+
+template <int S, bool RELU>
+__global__ void __launch_bounds__(ST_THREADS, 4)
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const StemTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem;                         // 2 x 16 KB
+  const uint32_t sB = smem + 2 * ST_A_BYTES;        // 4 KB
+  const uint32_t sO = sB + ST_B_BYTES;              // 2 x 8 KB
+  const uint32_t bar0 = sO + 2 * ST_O_BYTES;        // mma_done[2]
+  const uint32_t tmem_slot = bar0 + 16;
+  __shared__ float s_scale[ST_C], s_shift[ST_C];
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid < ST_C) {
+    s_scale[tid] = p.scale ? p.scale[tid] : 1.f;
+    s_shift[tid] = p.shift2[tid];
+  }
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
+    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // B tile: thread t < 32 writes filter row t (32 fp16 = 4 chunks) with the 128B swizzle
+  if (tid < ST_C) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.wq + tid * 32);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const uint4 v = __ldg(src + c);
+      sts128(sB + tid * 128 + ((c ^ (tid & 7)) << 4), v.x, v.y, v.z, v.w);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int Wo = p.ocols, HoWo = p.orows * p.ocols, W = p.cols, H = p.rows, ps = p.pix_stride;
+  const uint64_t descB = make_smem_desc(sB);
+  const long tiles = (p.m_total + 127) / 128;
+
+  // epilogue of tile j (runs one iteration late so the MMA round trip is hidden behind a gather)
+  auto epilogue = [&](long j_tile, int j) {
+    const int buf = j & 1;
+    mbar_wait(bar0 + 8 * buf, (uint32_t)(j >> 1) & 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t v[32];
+    {
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * ST_C);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+    const uint32_t orow = sO + buf * ST_O_BYTES + tid * 64;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int ch = c * 8 + e * 2;
+        pk[e] = pack2<RELU>(fmaf(__uint_as_float(v[ch]), s_scale[ch], s_shift[ch]),
+                            fmaf(__uint_as_float(v[ch + 1]), s_scale[ch + 1], s_shift[ch + 1]), p.cap2);
+      }
+      sts128(orow + ((c ^ ((tid >> 1) & 3)) << 4), pk[0], pk[1], pk[2], pk[3]);   // SWIZZLE_64B
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_out),
+                   "r"(sO + buf * ST_O_BYTES), "r"(0), "r"((int)(j_tile * 128))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  };
+
+  int i = 0;
+  long prev_tile = -1;
+  for (long t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+    const int buf = i & 1;
+    // ---- gather the 27 taps of pixel m into row `tid` of A[buf]
+    const long m = t * 128 + tid;
+    uint32_t a[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[q] = 0u;
+    if (m < p.m_total) {
+      const int img = (int)(m / HoWo);
+      const int rem = (int)(m - (long)img * HoWo);
+      const int oy = rem / Wo, ox = rem - oy * Wo;
+      const int iy0 = oy * S - p.pad_lo, ix0 = ox * S - p.pad_lo;
+      const uint8_t* planes[3] = {p.r + (long)img * p.img_stride, p.g + (long)img * p.img_stride,
+                                  p.b + (long)img * p.img_stride};
+      const bool interior = iy0 >= 0 && ix0 >= 0 && iy0 + 2 < H && ix0 + 2 < W;
+      uint32_t tap[28];
+      tap[27] = 0;
+      if (interior) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          const uint8_t* base = planes[pl] + ((long)iy0 * W + ix0) * ps;
+#pragma unroll
+          for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) tap[pl * 9 + ii * 3 + jj] = __ldg(base + ((long)ii * W + jj) * ps);
+        }
+#pragma unroll
+        for (int q = 0; q < 13; ++q) a[q] = u8x2_to_f16x2(tap[2 * q], tap[2 * q + 1]);
+        a[13] = u8x2_to_f16x2(tap[26], 0u) & 0x0000ffffu;
+      } else {
+        // border pixel: out-of-range taps read p0 (the raw value whose transform is zero)
+        unsigned short hv[28];
+        const unsigned short padv = (unsigned short)(p.pad_f16x2 & 0xffffu);
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+          for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+              const int y = iy0 + ii, x = ix0 + jj;
+              unsigned short h = padv;
+              if (y >= 0 && y < H && x >= 0 && x < W)
+                h = __half_as_ushort(__ushort2half_rn((unsigned short)__ldg(planes[pl] + ((long)y * W + x) * ps)));
+              hv[pl * 9 + ii * 3 + jj] = h;
+            }
+        hv[27] = 0;
+#pragma unroll
+        for (int q = 0; q < 14; ++q) a[q] = (uint32_t)hv[2 * q] | ((uint32_t)hv[2 * q + 1] << 16);
+      }
+    }
+    {
+      const uint32_t arow = sA + buf * ST_A_BYTES + tid * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sts128(arow + ((c ^ (tid & 7)) << 4), a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // staging buffer reuse
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint64_t descA = make_smem_desc(sA + buf * ST_A_BYTES);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(buf * ST_C);
+      umma_f16(tmem_d, descA, descB, 0u);            // k = 0..15
+      umma_f16(tmem_d, descA + 2, descB + 2, 1u);    // k = 16..31
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * buf) : "memory");
+    }
+    if (i > 0) epilogue(prev_tile, i - 1);
+    prev_tile = t;
+  }
+  if (i > 0) epilogue(prev_tile, i - 1);
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+}  // namespace
+
+// Host-side preparation of the fp16 filter bank and folded shift for a given input transform.
+// wq_dev: [32][32] fp16, shift2_dev: [32] fp32 (both device, caller-allocated).
+cudaError_t stem_tc_prepare(const float* w_oihw_host, const float* scale_host, const float* shift_host,
+                            float in_scale, float in_bias, __half* wq_dev, float* shift2_dev, float* p0_out) {
+  if (in_scale == 0.f) return cudaErrorInvalidValue;
+  const float p0 = -in_bias / in_scale;
+  const float p0h = __half2float(__float2half_rn(p0));
+  __half wq[32 * 32];
+  float shift2[32];
+  for (int o = 0; o < 32; ++o) {
+    double sum = 0.0;
+    for (int k = 0; k < 32; ++k) {
+      const float v = k < 27 ? w_oihw_host[o * 27 + k] * in_scale : 0.f;
+      wq[o * 32 + k] = __float2half_rn(v);
+      sum += (double)__half2float(wq[o * 32 + k]);
+    }
+    const double sc = scale_host ? scale_host[o] : 1.0, sh = shift_host ? shift_host[o] : 0.0;
+    shift2[o] = (float)(sh + sc * (-(double)p0h * sum));
+  }
+  cudaError_t e = cudaMemcpy(wq_dev, wq, sizeof wq, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(shift2_dev, shift2, sizeof shift2, cudaMemcpyHostToDevice);
+  if (p0_out) *p0_out = p0h;
+  return e;
+}
+
+cudaError_t launch_stem_tc(bf16* out, const StemArgs& a, const __half* wq_dev, const float* scale_dev,
+                           const float* shift2_dev, float p0, int act, int num_sms, cudaStream_t st,
+                           std::string* err) {
+  if (a.cout != ST_C || (a.stride != 1 && a.stride != 2)) return cudaErrorNotSupported;
+  if (a.n <= 0) return cudaSuccess;
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { if (err) *err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
+  StemTcParams p{};
+  p.r = a.r; p.g = a.g; p.b = a.b; p.pix_stride = a.pix_stride; p.img_stride = a.img_stride;
+  p.n = a.n; p.rows = a.rows; p.cols = a.cols; p.orows = a.rows / a.stride; p.ocols = a.cols / a.stride;
+  p.pad_lo = a.pad_lo; p.wq = wq_dev; p.scale = scale_dev; p.shift2 = shift2_dev;
+  p.cap2 = act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
+  const unsigned short ph = __half_as_ushort(__float2half_rn(p0));
+  p.pad_f16x2 = (uint32_t)ph | ((uint32_t)ph << 16);
+  p.m_total = (long)a.n * p.orows * p.ocols;
+  CUtensorMap tm;
+  cuuint64_t gdim[2] = {(cuuint64_t)ST_C, (cuuint64_t)p.m_total};
+  cuuint64_t gstr[1] = {(cuuint64_t)ST_C * 2};
+  cuuint32_t box[2] = {(cuuint32_t)ST_C, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) { char b[128]; snprintf(b, sizeof b, "stem output tensor map encode failed (CUresult %d)", (int)r); *err = b; }
+    return cudaErrorInvalidValue;
+  }
+  const size_t smem = 1024 + 2 * ST_A_BYTES + ST_B_BYTES + 2 * ST_O_BYTES + 64;
+  const long tiles = (p.m_total + 127) / 128;
+  long grid = (long)num_sms * 4;
+  if (grid > tiles) grid = tiles;
+  const bool relu = act != MNV1_ACT_NONE;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaSuccess;
+    auto set = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
+    set((const void*)stem_tc_kernel<1, true>); set((const void*)stem_tc_kernel<1, false>);
+    set((const void*)stem_tc_kernel<2, true>); set((const void*)stem_tc_kernel<2, false>);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+#define ST_LAUNCH(S, R) stem_tc_kernel<S, R><<<(unsigned)grid, ST_THREADS, smem, st>>>(tm, p)
+  if (a.stride == 2) { if (relu) ST_LAUNCH(2, true); else ST_LAUNCH(2, false); }
+  else               { if (relu) ST_LAUNCH(1, true); else ST_LAUNCH(1, false); }
+#undef ST_LAUNCH
+  return cudaGetLastError();
+}
+
+}  // namespace mnv1

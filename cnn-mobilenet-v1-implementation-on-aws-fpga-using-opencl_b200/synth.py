@@ -95,3 +95,25 @@ def kat_ints(seed: int, count: int, lo: int, hi: int) -> np.ndarray:
     """Small integers in [lo, hi] for the bit-exact known-answer tests."""
     w = splitmix64(seed, np.arange(count, dtype=np.uint64))
     return lo + ((w >> np.uint64(33)) % np.uint64(hi - lo + 1)).astype(np.int64)
+
+
+def _round_bf16(x: np.ndarray) -> np.ndarray:
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(np.shape(x))
+
+
+def bf16_storage_weights(w: np.ndarray, in_scale: float = 1.0 / 127.5) -> np.ndarray:
+    """The filter values a bf16 context actually multiplies with (csrc/api.cu, stem_tc.cu):
+    pointwise and FC filters are stored in bf16; the stem's taps are folded with the input scale
+    and stored in fp16 (returned here divided by the scale again); depthwise taps stay fp32."""
+    from .layers import LAYERS, POINTWISE, FC, STEM
+    out = np.array(w, dtype=np.float32, copy=True)
+    for L in LAYERS:
+        sl = slice(L.w_off, L.w_off + L.w_cnt)
+        if L.kind in (POINTWISE, FC):
+            out[sl] = _round_bf16(out[sl])
+        elif L.kind == STEM:
+            s = np.float32(in_scale)
+            out[sl] = (out[sl] * s).astype(np.float16).astype(np.float32) / s
+    return out

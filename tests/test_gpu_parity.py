@@ -156,7 +156,10 @@ def test_stem_layer(ctx, mn, oracle_mod, pad):
     w = (rng.standard_normal((32, 3, 3, 3)) * np.sqrt(2.0 / 27)).astype(np.float32)
     sc = (0.5 + rng.random(32)).astype(np.float32)
     sh = (rng.standard_normal(32) * 0.1).astype(np.float32)
-    want = oracle_mod.convolute(img, img.reshape(-1)[1:], img.reshape(-1)[2:], w, n, 224, 224, 2, 32, pad_mode=pad,
+    wo = w
+    if ctx.dtype == mn.BF16:  # the tensor-core stem stores fp16(w * in_scale)
+        wo = ((w * np.float32(1 / 127.5)).astype(np.float16).astype(np.float32) / np.float32(1 / 127.5))
+    want = oracle_mod.convolute(img, img.reshape(-1)[1:], img.reshape(-1)[2:], wo, n, 224, 224, 2, 32, pad_mode=pad,
                                 in_scale=1 / 127.5, in_bias=-1.0, scale=sc, shift=sh, act=oracle_mod.ACT_RELU6,
                                 rbf16=ctx.dtype == mn.BF16, pix_stride=3, img_stride=224 * 224 * 3)
     ctx.set_pad_mode(pad)
@@ -242,12 +245,8 @@ def test_bf16_network(mn, oracle_mod, synth_net):
     max(1,|ref|)); logits within 0.05 absolute (logit spread is ~0.8); identical top-1
     wherever the oracle's top-1 margin exceeds 0.1."""
     from mnv1_b200 import synth
-    from mnv1_b200.layers import LAYERS, POINTWISE, FC
     w, sc, sh = synth_net
-    wq = w.copy()
-    for L in LAYERS:
-        if L.kind in (POINTWISE, FC):
-            wq[L.w_off:L.w_off + L.w_cnt] = oracle_mod.round_bf16(w[L.w_off:L.w_off + L.w_cnt])
+    wq = synth.bf16_storage_weights(w)  # bf16 pointwise/FC filters, fp16 scale-folded stem taps
     n = 4
     img = synth.images(n)
     logits, taps = oracle_mod.forward(img, wq, sc, sh, rbf16=1, taps=(1, 2, 3, 5, 13, 27))
