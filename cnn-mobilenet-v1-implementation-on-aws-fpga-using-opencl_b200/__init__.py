@@ -4,4 +4,4 @@ The product is ``libmnv1.so`` (csrc/, C-ABI in include/mnv1.h).  This Python pac
 the thin host-side mirror used by the tests and bench: layer schedule, synthetic data,
 ctypes binding.  It never imports anything from ``oracle/``.
 """
-from . import layers, synth, binding  # noqa: F401
+from . import layers, synth, binding, shard  # noqa: F401

@@ -611,6 +611,17 @@ int mnv1_load_weights(mnv1_ctx* ctx, const char* path, mnv1_act act) {
   if (rc) return fail(ctx, rc, err);
   return mnv1_set_weights(ctx, w.data(), sc.data(), sh.data(), act);
 }
+int mnv1_parse_weights(const char* path, float* weights, float* scale, float* shift) {
+  if (!path || !weights) return fail(nullptr, MNV1_EINVAL, "parse_weights: null argument");
+  std::vector<float> w, sc, sh;
+  std::string err;
+  int rc = mnv1::load_weight_file(path, &w, &sc, &sh, &err);
+  if (rc) return fail(nullptr, rc, err);
+  memcpy(weights, w.data(), w.size() * 4);
+  if (scale) memcpy(scale, sc.data(), sc.size() * 4);
+  if (shift) memcpy(shift, sh.data(), sh.size() * 4);
+  return MNV1_OK;
+}
 int mnv1_save_weights_bin(const char* path, const float* weights, const float* scale, const float* shift) {
   if (!path || !weights) return fail(nullptr, MNV1_EINVAL, "save_weights_bin: null argument");
   std::string err;

@@ -58,14 +58,15 @@ cudaError_t launch_pool(mnv1_dtype dt, void* out, const void* in, int n, int hw,
 }
 
 // FC (MobileNet.c:2681-2763): logits[img][cls] = bias[cls] + sum_k pooled[img][k] * w[cls][k].
-// A CTA holds the pooled vectors of 16 images in shared memory (fp32) and owns 64 classes; each
-// warp walks 8 filter rows: lanes stride the contraction (coalesced 16-byte filter loads, each
-// filter value reused for the 16 images), then a warp-shuffle tree folds the 32 partial sums.
-constexpr int FC_IMGS = 16, FC_CLS = 64;
+// A CTA holds the pooled vectors of 8 images in shared memory (fp32) and owns 64 classes; a warp
+// owns 8 filter rows at once.  Per 256-wide k step a lane loads 8 filter values per row (kept in
+// registers, 64 in all) and streams the 8 images past them: 2 conflict-free LDS.128 feed 64 FFMA.
+// A warp-shuffle tree folds the 32 per-lane partial sums of the 8 x 8 outputs at the end.
+constexpr int FC_IMGS = 8, FC_CLS = 64, FC_WCLS = 8;
 template <typename TW>
-__global__ void __launch_bounds__(256) fc_kernel(float* __restrict__ out, const float* __restrict__ pooled,
-                                                 const TW* __restrict__ w, const float* __restrict__ bias, int n, int k,
-                                                 int classes) {
+__global__ void __launch_bounds__(256, 1) fc_kernel(float* __restrict__ out, const float* __restrict__ pooled,
+                                                    const TW* __restrict__ w, const float* __restrict__ bias, int n,
+                                                    int k, int classes) {
   extern __shared__ float s_a[];  // [FC_IMGS][k]
   const int img0 = blockIdx.y * FC_IMGS, cls0 = blockIdx.x * FC_CLS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,42 +77,64 @@ __global__ void __launch_bounds__(256) fc_kernel(float* __restrict__ out, const 
     *reinterpret_cast<float4*>(&s_a[i]) = v;
   }
   __syncthreads();
-  for (int c = 0; c < FC_CLS / 8; ++c) {
-    const int cls = cls0 + warp * (FC_CLS / 8) + c;
-    if (cls >= classes) break;
-    float acc[FC_IMGS];
+  const int clsw = cls0 + warp * FC_WCLS;
+  float acc[FC_WCLS][FC_IMGS];
 #pragma unroll
-    for (int im = 0; im < FC_IMGS; ++im) acc[im] = 0.f;
-    for (int kk = lane * 8; kk < k; kk += 256) {
-      float wv[8];
+  for (int c = 0; c < FC_WCLS; ++c)
+#pragma unroll
+    for (int im = 0; im < FC_IMGS; ++im) acc[c][im] = 0.f;
+  for (int k0 = 0; k0 < k; k0 += 256) {
+    // this lane's 8 contraction indices of the step: k0 + lane*4 + {0..3} and + 128
+    const int ka = k0 + lane * 4, kb = ka + 128;
+    float wv[FC_WCLS][8];
+#pragma unroll
+    for (int c = 0; c < FC_WCLS; ++c) {
+      const int cls = min(clsw + c, classes - 1);  // clamp: rows past the end are computed but never stored
       if constexpr (sizeof(TW) == 2) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(w + (long)cls * k + kk));
-        wv[0] = bf16lo_to_f32(raw.x); wv[1] = bf16hi_to_f32(raw.x); wv[2] = bf16lo_to_f32(raw.y); wv[3] = bf16hi_to_f32(raw.y);
-        wv[4] = bf16lo_to_f32(raw.z); wv[5] = bf16hi_to_f32(raw.z); wv[6] = bf16lo_to_f32(raw.w); wv[7] = bf16hi_to_f32(raw.w);
+        const uint2 r0 = __ldg(reinterpret_cast<const uint2*>(w + (long)cls * k + ka));
+        const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(w + (long)cls * k + kb));
+        wv[c][0] = bf16lo_to_f32(r0.x); wv[c][1] = bf16hi_to_f32(r0.x); wv[c][2] = bf16lo_to_f32(r0.y); wv[c][3] = bf16hi_to_f32(r0.y);
+        wv[c][4] = bf16lo_to_f32(r1.x); wv[c][5] = bf16hi_to_f32(r1.x); wv[c][6] = bf16lo_to_f32(r1.y); wv[c][7] = bf16hi_to_f32(r1.y);
       } else {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(w + (long)cls * k + kk));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(w + (long)cls * k + kk + 4));
-        wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
-      }
-#pragma unroll
-      for (int im = 0; im < FC_IMGS; ++im) {
-        const float4 a0 = *reinterpret_cast<const float4*>(&s_a[im * k + kk]);
-        const float4 a1 = *reinterpret_cast<const float4*>(&s_a[im * k + kk + 4]);
-        acc[im] = fmaf(a0.x, wv[0], fmaf(a0.y, wv[1], fmaf(a0.z, wv[2], fmaf(a0.w, wv[3], acc[im]))));
-        acc[im] = fmaf(a1.x, wv[4], fmaf(a1.y, wv[5], fmaf(a1.z, wv[6], fmaf(a1.w, wv[7], acc[im]))));
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(w + (long)cls * k + ka));
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(w + (long)cls * k + kb));
+        wv[c][0] = r0.x; wv[c][1] = r0.y; wv[c][2] = r0.z; wv[c][3] = r0.w;
+        wv[c][4] = r1.x; wv[c][5] = r1.y; wv[c][6] = r1.z; wv[c][7] = r1.w;
       }
     }
 #pragma unroll
     for (int im = 0; im < FC_IMGS; ++im) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&s_a[im * k + ka]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&s_a[im * k + kb]);
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) acc[im] += __shfl_xor_sync(0xffffffffu, acc[im], off);
+      for (int c = 0; c < FC_WCLS; ++c) {
+        float t = acc[c][im];
+        t = fmaf(a0.x, wv[c][0], t); t = fmaf(a0.y, wv[c][1], t); t = fmaf(a0.z, wv[c][2], t); t = fmaf(a0.w, wv[c][3], t);
+        t = fmaf(a1.x, wv[c][4], t); t = fmaf(a1.y, wv[c][5], t); t = fmaf(a1.z, wv[c][6], t); t = fmaf(a1.w, wv[c][7], t);
+        acc[c][im] = t;
+      }
     }
-    if (lane < FC_IMGS && img0 + lane < n) {
-      float v = acc[0];
+  }
+  // fold the 32 lanes; lane (c*8 + im) ends up owning output (class c, image im)
+  float mine = 0.f, mine2 = 0.f;
 #pragma unroll
-      for (int im = 1; im < FC_IMGS; ++im) v = lane == im ? acc[im] : v;
-      out[(long)(img0 + lane) * classes + cls] = v + (bias ? __ldg(bias + cls) : 0.f);
+  for (int c = 0; c < FC_WCLS; ++c)
+#pragma unroll
+    for (int im = 0; im < FC_IMGS; ++im) {
+      float v = acc[c][im];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == ((c * FC_IMGS + im) & 31)) {
+        if (c * FC_IMGS + im < 32) mine = v; else mine2 = v;
+      }
     }
+  // lane L now holds outputs L (mine) and 32 + L (mine2)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int idx = h * 32 + lane, c = idx / FC_IMGS, im = idx % FC_IMGS;
+    const int cls = clsw + c;
+    const float v = h == 0 ? mine : mine2;
+    if (cls < classes && img0 + im < n) out[(long)(img0 + im) * classes + cls] = v + (bias ? __ldg(bias + cls) : 0.f);
   }
 }
 
@@ -121,6 +144,7 @@ cudaError_t launch_fc(float* out, const float* pooled, const float* w_f32, const
   if (k % 256) return cudaErrorNotSupported;
   dim3 grid((classes + FC_CLS - 1) / FC_CLS, (n + FC_IMGS - 1) / FC_IMGS);
   const size_t smem = (size_t)FC_IMGS * k * sizeof(float);
+  if (k % 256 || smem > 96 * 1024) return cudaErrorNotSupported;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(fc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

@@ -134,6 +134,9 @@ int mnv1_set_weights(mnv1_ctx* ctx, const float* weights, const float* scale, co
 int mnv1_load_weights(mnv1_ctx* ctx, const char* path, mnv1_act act);
 int mnv1_save_weights_bin(const char* path, const float* weights, const float* scale,
                           const float* shift);
+/* host-only parse of a weight file (text or binary) into caller arrays: weights
+ * [MNV1_TOTAL_WEIGHTS], scale / shift [MNV1_BN_CHANNELS + 1000].  Needs no GPU. */
+int mnv1_parse_weights(const char* path, float* weights, float* scale, float* shift);
 /* P6 PPM reader that skips the header (fixes SURVEY App. C D-15); out = 224*224*3 bytes */
 int mnv1_read_ppm(const char* path, uint8_t* out_rgb, int height, int width);
 /* allocate the activation arena for batches up to max_batch and capture the CUDA graph */

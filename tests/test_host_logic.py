@@ -1,0 +1,121 @@
+"""Host-side logic that needs no GPU: the layer schedule, the C-ABI library's exports, weight
+and image file readers, error behaviour without a device, the batch sharding."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import mnv1_b200  # noqa: F401
+from mnv1_b200 import binding as mn, layers, shard, synth
+
+
+def test_layer_schedule_matches_the_reference_counts():
+    L = layers.LAYERS
+    assert len(L) == 29 and layers.TOTAL_WEIGHTS == 4209088 and layers.BN_CHANNELS == 10944
+    # readSquezeNetKernel counts, SURVEY App. A column nW (MobileNet.c:241,337,419,...,2696)
+    nw = [864, 288, 2048, 576, 8192, 1152, 16384, 1152, 32768, 2304, 65536, 2304, 131072] + \
+         [4608, 262144] * 5 + [4608, 524288, 9216, 1048576, 0, 1024000]
+    assert [l.w_cnt for l in L] == nw
+    assert sum(l.w_cnt for l in L[:5]) == 11968 and sum(l.w_cnt for l in L[:13]) == 264640
+    assert abs(sum(2 * l.macs for l in L) / 1e6 - 1137.53) < 0.1  # MFLOP per image
+    assert sum(l.in_elems + l.out_elems for l in L) == 10238952
+    assert [l.hout for l in L[:5]] == [112, 112, 112, 56, 56] and L[25].stride == 1
+
+
+def test_library_exports_every_declared_symbol():
+    lib = mn.lib()
+    syms = mn.declared_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert b"sm_100a" in lib.mnv1_version()
+
+
+def test_layer_table_from_the_library_agrees_with_python():
+    class Info(C.Structure):
+        _fields_ = [(n, C.c_int) for n in ("index", "kind", "cin", "cout", "hin", "hout", "stride")] + \
+                   [(n, C.c_long) for n in ("w_off", "w_cnt", "c_off")]
+    arr = (Info * 29)()
+    assert mn.lib().mnv1_layer_table(arr) == 0
+    for a, b in zip(arr, layers.LAYERS):
+        assert (a.index, a.kind, a.cin, a.cout, a.hin, a.hout, a.stride, a.w_off, a.w_cnt, a.c_off) == \
+               (b.index, b.kind, b.cin, b.cout, b.hin, b.hout, b.stride, b.w_off, b.w_cnt, b.c_off)
+
+
+def test_no_gpu_means_a_loud_error_not_a_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(mn.Mnv1Error) as e:
+        mn.Context(0, mn.BF16)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def _parse(path):
+    w = np.empty(layers.TOTAL_WEIGHTS, np.float32)
+    sc = np.empty(layers.TOTAL_CHANNELS, np.float32)
+    sh = np.empty(layers.TOTAL_CHANNELS, np.float32)
+    rc = mn.lib().mnv1_parse_weights(path.encode(), w.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
+                                     sh.ctypes.data_as(C.c_void_p))
+    return rc, w, sc, sh
+
+
+def test_weight_file_round_trip_binary_and_text(tmp_path, synth_net):
+    w, sc, sh = synth_net
+    p = str(tmp_path / "w.bin")
+    assert mn.lib().mnv1_save_weights_bin(p.encode(), w.ctypes.data_as(C.c_void_p), sc.ctypes.data_as(C.c_void_p),
+                                          sh.ctypes.data_as(C.c_void_p)) == 0
+    rc, w2, sc2, sh2 = _parse(p)
+    assert rc == 0 and np.array_equal(w, w2) and np.array_equal(sc, sc2) and np.array_equal(sh, sh2)
+    # the reference's text format: whitespace separated decimals (MobileNet.c:37-44), filters only
+    t = str(tmp_path / "weights_c.txt")
+    wi = synth.kat_ints(3, layers.TOTAL_WEIGHTS, -5, 5).astype(np.float32)
+    with open(t, "w") as f:
+        f.write(" ".join("%d" % v for v in wi[:1000]) + "\n")
+        np.savetxt(f, wi[1000:], fmt="%.1f", newline=" ")
+    rc, w3, sc3, sh3 = _parse(t)
+    assert rc == 0 and np.array_equal(w3, wi) and np.all(sc3 == 1) and np.all(sh3 == 0)
+    # wrong token count -> MNV1_EIO with a message, not garbage weights
+    with open(t, "w") as f:
+        f.write("1 2 3")
+    rc, *_ = _parse(t)
+    assert rc == -4 and b"tokens" in mn.lib().mnv1_last_error(None)
+    rc, *_ = _parse(str(tmp_path / "missing.txt"))
+    assert rc == -4
+
+
+def test_ppm_reader_skips_the_header(tmp_path):
+    img = synth.images(1)[0]
+    p = str(tmp_path / "Cat_Image0.ppm")
+    with open(p, "wb") as f:
+        f.write(b"P6\n# made by the test\n224 224\n255\n" + img.tobytes())
+    out = np.zeros((224, 224, 3), np.uint8)
+    assert mn.lib().mnv1_read_ppm(p.encode(), out.ctypes.data_as(C.c_void_p), 224, 224) == 0
+    assert np.array_equal(out, img)  # decode_image (MobileNet.c:49-57) would have read the header as pixels
+    with open(p, "wb") as f:
+        f.write(b"P6\n100 100\n255\n" + bytes(30000))
+    assert mn.lib().mnv1_read_ppm(p.encode(), out.ctypes.data_as(C.c_void_p), 224, 224) == -4
+
+
+def test_shard_ranges_cover_the_batch():
+    for n, g in [(2048, 8), (2048, 4), (256, 1), (10, 4), (3, 8), (0, 2)]:
+        spans = [shard.shard_range(n, r, g) for r in range(g)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+    assert shard.shard_range(2048, 3, 8) == (768, 1024)
+    with pytest.raises(ValueError):
+        shard.shard_range(8, 8, 8)
+
+
+def test_bf16_storage_weights():
+    w = synth.weights()
+    q = synth.bf16_storage_weights(w)
+    L = layers.LAYERS
+    assert np.array_equal(q[L[1].w_off:L[1].w_off + L[1].w_cnt], w[L[1].w_off:L[1].w_off + L[1].w_cnt])  # depthwise fp32
+    pw = q[L[2].w_off:L[2].w_off + L[2].w_cnt]
+    assert np.all((pw.view(np.uint32) & 0xFFFF) == 0)  # bf16-representable
+    assert np.max(np.abs(pw - w[L[2].w_off:L[2].w_off + L[2].w_cnt]) / np.abs(w[L[2].w_off:L[2].w_off + L[2].w_cnt])) <= 2 ** -8
+    st = slice(L[0].w_off, L[0].w_off + L[0].w_cnt)  # stem: fp16 (11 significant bits) after folding 1/127.5
+    assert np.max(np.abs(q[st] - w[st])) <= 2.0 ** -11 * np.max(np.abs(w[st]))
