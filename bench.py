@@ -177,7 +177,8 @@ def run_ours(args):
         # keep the GPU busy a little longer so the clock sampler sees the loaded state on short runs
         t_extra = time.time()
         while rank == 0 and len(sampler.lines) < 3 and time.time() - t_extra < 1.5:
-            step(0)
+            # rank-local work only (no collective: the other ranks are not in this loop)
+            ctx.forward_device(imgs[0].data_ptr(), batch, logits.data_ptr(), top1.data_ptr(), prob.data_ptr())
             torch.cuda.synchronize(dev)
         clocks = sampler.stop() if rank == 0 else None
         tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -277,7 +278,12 @@ def cpu_reference(sample_images: int, steps: int):
     import mnv1_b200  # noqa: F401
     from mnv1_b200 import synth
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ["OMP_NUM_THREADS"] = str(cores)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every core
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
     sample_images = min(512, max(sample_images, cores))  # one image per host thread at least
     img = synth.images(sample_images)
     lit = oracle.literal()
