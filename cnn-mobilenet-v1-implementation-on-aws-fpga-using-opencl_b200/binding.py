@@ -254,6 +254,16 @@ class Context:
         self._ck(lib().mnv1_forward(self.h, C.c_void_p(images_ptr), n, C.c_void_p(logits_ptr), C.c_void_p(top1_ptr),
                                     C.c_void_p(prob_ptr)))
 
+    def forward_submit(self, images_ptr: int, n: int, logits_ptr: int, top1_ptr: int, prob_ptr: int) -> int:
+        """Pipelined mnv1_forward: returns a ticket; up to two batches in flight."""
+        t = C.c_long(-1)
+        self._ck(lib().mnv1_forward_submit(self.h, C.c_void_p(images_ptr), n, C.c_void_p(logits_ptr or None),
+                                           C.c_void_p(top1_ptr or None), C.c_void_p(prob_ptr or None), C.byref(t)))
+        return t.value
+
+    def forward_wait(self, ticket: int):
+        self._ck(lib().mnv1_forward_wait(self.h, C.c_long(ticket)))
+
     def forward_device(self, d_images: int, n: int, d_logits: int, d_top1: int = 0, d_prob: int = 0):
         self._ck(lib().mnv1_forward_device(self.h, C.c_void_p(d_images), n, C.c_void_p(d_logits),
                                            C.c_void_p(d_top1 or None), C.c_void_p(d_prob or None)))

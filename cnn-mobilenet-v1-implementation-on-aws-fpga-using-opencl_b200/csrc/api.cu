@@ -79,10 +79,21 @@ struct mnv1_ctx {
   float* d_logits = nullptr;
   int* d_top1 = nullptr;
   float* d_prob = nullptr;
-  uint8_t* h_images = nullptr;  // pinned staging
+  uint8_t* h_images = nullptr;  // pinned staging (slot 0; aliases of slots[0])
   float* h_logits = nullptr;
   int* h_top1 = nullptr;
   float* h_prob = nullptr;
+  // two in-flight batches for mnv1_forward_submit / _wait: while batch i computes, batch i+1's
+  // images are copied in (copy stream) and batch i-1's results are copied out (d2h stream)
+  struct Slot {
+    uint8_t* d_images = nullptr; float* d_logits = nullptr; int* d_top1 = nullptr; float* d_prob = nullptr;
+    uint8_t* h_images = nullptr; float* h_logits = nullptr; int* h_top1 = nullptr; float* h_prob = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_done = nullptr;
+    bool busy = false; int n = 0; long ticket = -1;
+    float* u_logits = nullptr; int* u_top1 = nullptr; float* u_prob = nullptr;  // unpinned user outputs
+  } slots[2];
+  cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+  long next_ticket = 0;
   std::map<GraphKey, cudaGraphExec_t> graphs;
   bool use_graph = true;
 };
@@ -144,6 +155,8 @@ int mnv1_ctx_create(int device, mnv1_dtype dtype, mnv1_ctx** out) {
   ctx->dtype = dtype;
   ctx->num_sms = prop.multiProcessorCount;
   CK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(nullptr, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CK(nullptr, cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
   CK(nullptr, cudaEventCreate(&ctx->ev0));
   CK(nullptr, cudaEventCreate(&ctx->ev1));
   *out = ctx.release();
@@ -154,12 +167,17 @@ static void free_plan(mnv1_ctx* ctx) {
   for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
   ctx->graphs.clear();
   for (int i = 0; i < 2; ++i) { cudaFree(ctx->act[i]); ctx->act[i] = nullptr; }
-  cudaFree(ctx->d_images); cudaFree(ctx->d_pooled); cudaFree(ctx->d_logits); cudaFree(ctx->d_top1);
-  cudaFree(ctx->d_prob);
-  cudaFreeHost(ctx->h_images); cudaFreeHost(ctx->h_logits); cudaFreeHost(ctx->h_top1); cudaFreeHost(ctx->h_prob);
-  ctx->d_images = nullptr; ctx->d_pooled = nullptr; ctx->d_logits = nullptr; ctx->d_top1 = nullptr;
-  ctx->d_prob = nullptr; ctx->h_images = nullptr; ctx->h_logits = nullptr; ctx->h_top1 = nullptr;
-  ctx->h_prob = nullptr;
+  cudaFree(ctx->d_pooled); ctx->d_pooled = nullptr;
+  for (auto& sl : ctx->slots) {
+    cudaFree(sl.d_images); cudaFree(sl.d_logits); cudaFree(sl.d_top1); cudaFree(sl.d_prob);
+    cudaFreeHost(sl.h_images); cudaFreeHost(sl.h_logits); cudaFreeHost(sl.h_top1); cudaFreeHost(sl.h_prob);
+    if (sl.ev_h2d) cudaEventDestroy(sl.ev_h2d);
+    if (sl.ev_compute) cudaEventDestroy(sl.ev_compute);
+    if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+    sl = mnv1_ctx::Slot();
+  }
+  ctx->d_images = nullptr; ctx->d_logits = nullptr; ctx->d_top1 = nullptr; ctx->d_prob = nullptr;
+  ctx->h_images = nullptr; ctx->h_logits = nullptr; ctx->h_top1 = nullptr; ctx->h_prob = nullptr;
   ctx->plan_batch = 0;
 }
 
@@ -174,6 +192,8 @@ int mnv1_ctx_destroy(mnv1_ctx* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   delete ctx;
   return MNV1_OK;
 }
@@ -648,15 +668,24 @@ int mnv1_plan(mnv1_ctx* ctx, int max_batch) {
   const size_t act_bytes = (size_t)max_batch * kMaxActElems * elem_size(ctx->dtype);
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&ctx->act[i], act_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_images, (size_t)max_batch * kImgBytes);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_pooled, (size_t)max_batch * 1024 * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_logits, (size_t)max_batch * MNV1_NUM_CLASSES * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_top1, (size_t)max_batch * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_prob, (size_t)max_batch * 4);
-  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_images, (size_t)max_batch * kImgBytes);
-  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_logits, (size_t)max_batch * MNV1_NUM_CLASSES * 4);
-  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_top1, (size_t)max_batch * 4);
-  if (e == cudaSuccess) e = cudaMallocHost(&ctx->h_prob, (size_t)max_batch * 4);
+  for (auto& sl : ctx->slots) {
+    if (e == cudaSuccess) e = cudaMalloc(&sl.d_images, (size_t)max_batch * kImgBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.d_logits, (size_t)max_batch * MNV1_NUM_CLASSES * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.d_top1, (size_t)max_batch * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&sl.d_prob, (size_t)max_batch * 4);
+    if (e == cudaSuccess) e = cudaMallocHost(&sl.h_images, (size_t)max_batch * kImgBytes);
+    if (e == cudaSuccess) e = cudaMallocHost(&sl.h_logits, (size_t)max_batch * MNV1_NUM_CLASSES * 4);
+    if (e == cudaSuccess) e = cudaMallocHost(&sl.h_top1, (size_t)max_batch * 4);
+    if (e == cudaSuccess) e = cudaMallocHost(&sl.h_prob, (size_t)max_batch * 4);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.ev_h2d, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.ev_compute, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming);
+  }
+  ctx->d_images = ctx->slots[0].d_images; ctx->d_logits = ctx->slots[0].d_logits;
+  ctx->d_top1 = ctx->slots[0].d_top1; ctx->d_prob = ctx->slots[0].d_prob;
+  ctx->h_images = ctx->slots[0].h_images; ctx->h_logits = ctx->slots[0].h_logits;
+  ctx->h_top1 = ctx->slots[0].h_top1; ctx->h_prob = ctx->slots[0].h_prob;
   if (e != cudaSuccess) {
     free_plan(ctx);
     return fail(ctx, MNV1_ENOMEM, std::string("plan: allocation failed: ") + cudaGetErrorString(e));
@@ -765,29 +794,75 @@ int mnv1_ctx_use_graph(mnv1_ctx* ctx, int on) {
   return MNV1_OK;
 }
 
-int mnv1_forward(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int* top1, float* top1_prob) {
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes pa;
+  if (cudaPointerGetAttributes(&pa, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return pa.type == cudaMemoryTypeHost;
+}
+
+static int finish_slot(mnv1_ctx* ctx, mnv1_ctx::Slot& sl) {
+  if (!sl.busy) return MNV1_OK;
+  CK(ctx, cudaEventSynchronize(sl.ev_done));
+  if (sl.u_logits) memcpy(sl.u_logits, sl.h_logits, (size_t)sl.n * MNV1_NUM_CLASSES * 4);
+  if (sl.u_top1) memcpy(sl.u_top1, sl.h_top1, (size_t)sl.n * 4);
+  if (sl.u_prob) memcpy(sl.u_prob, sl.h_prob, (size_t)sl.n * 4);
+  sl.busy = false;
+  return MNV1_OK;
+}
+
+int mnv1_forward_submit(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int* top1, float* top1_prob,
+                        long* ticket) {
   int rc = check_ready(ctx, n);
   if (rc) return rc;
-  if (!images) return fail(ctx, MNV1_EINVAL, "forward: images is null");
-  // stage through pinned memory unless the caller's buffer already is (cudaHostAlloc / cudaHostRegister)
-  cudaPointerAttributes pa;
+  if (!images || !ticket) return fail(ctx, MNV1_EINVAL, "forward_submit: images / ticket is null");
+  mnv1_ctx::Slot& sl = ctx->slots[ctx->next_ticket & 1];
+  if ((rc = finish_slot(ctx, sl)) != MNV1_OK) return rc;  // the batch submitted two calls ago
+  sl.n = n; sl.ticket = ctx->next_ticket;
+  // images: straight from the caller's buffer when it is page-locked, else through the slot's staging copy
   const uint8_t* src = images;
-  if (cudaPointerGetAttributes(&pa, images) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
-    cudaGetLastError();
-    memcpy(ctx->h_images, images, (size_t)n * kImgBytes);
-    src = ctx->h_images;
-  }
-  CK(ctx, cudaMemcpyAsync(ctx->d_images, src, (size_t)n * kImgBytes, cudaMemcpyHostToDevice, ctx->stream));
-  rc = mnv1_forward_device(ctx, ctx->d_images, n, ctx->d_logits, ctx->d_top1, ctx->d_prob);
+  if (!is_pinned(images)) { memcpy(sl.h_images, images, (size_t)n * kImgBytes); src = sl.h_images; }
+  CK(ctx, cudaMemcpyAsync(sl.d_images, src, (size_t)n * kImgBytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  CK(ctx, cudaEventRecord(sl.ev_h2d, ctx->copy_stream));
+  CK(ctx, cudaStreamWaitEvent(ctx->stream, sl.ev_h2d, 0));
+  rc = mnv1_forward_device(ctx, sl.d_images, n, sl.d_logits, sl.d_top1, sl.d_prob);
   if (rc) return rc;
-  if (logits) CK(ctx, cudaMemcpyAsync(ctx->h_logits, ctx->d_logits, (size_t)n * MNV1_NUM_CLASSES * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (top1) CK(ctx, cudaMemcpyAsync(ctx->h_top1, ctx->d_top1, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (top1_prob) CK(ctx, cudaMemcpyAsync(ctx->h_prob, ctx->d_prob, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(ctx, cudaStreamSynchronize(ctx->stream));
-  if (logits) memcpy(logits, ctx->h_logits, (size_t)n * MNV1_NUM_CLASSES * 4);
-  if (top1) memcpy(top1, ctx->h_top1, (size_t)n * 4);
-  if (top1_prob) memcpy(top1_prob, ctx->h_prob, (size_t)n * 4);
+  CK(ctx, cudaEventRecord(sl.ev_compute, ctx->stream));
+  CK(ctx, cudaStreamWaitEvent(ctx->d2h_stream, sl.ev_compute, 0));
+  sl.u_logits = nullptr; sl.u_top1 = nullptr; sl.u_prob = nullptr;
+  if (logits) {
+    float* dst = logits;
+    if (!is_pinned(logits)) { dst = sl.h_logits; sl.u_logits = logits; }
+    CK(ctx, cudaMemcpyAsync(dst, sl.d_logits, (size_t)n * MNV1_NUM_CLASSES * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  }
+  if (top1) {
+    int* dst = top1;
+    if (!is_pinned(top1)) { dst = sl.h_top1; sl.u_top1 = top1; }
+    CK(ctx, cudaMemcpyAsync(dst, sl.d_top1, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  }
+  if (top1_prob) {
+    float* dst = top1_prob;
+    if (!is_pinned(top1_prob)) { dst = sl.h_prob; sl.u_prob = top1_prob; }
+    CK(ctx, cudaMemcpyAsync(dst, sl.d_prob, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  }
+  CK(ctx, cudaEventRecord(sl.ev_done, ctx->d2h_stream));
+  sl.busy = true;
+  *ticket = ctx->next_ticket++;
   return MNV1_OK;
+}
+
+int mnv1_forward_wait(mnv1_ctx* ctx, long ticket) {
+  if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
+  mnv1_ctx::Slot& sl = ctx->slots[ticket & 1];
+  if (ticket < 0 || ticket >= ctx->next_ticket) return fail(ctx, MNV1_EINVAL, "forward_wait: unknown ticket");
+  if (sl.ticket != ticket) return MNV1_OK;  // already retired by a later submit
+  return finish_slot(ctx, sl);
+}
+
+int mnv1_forward(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int* top1, float* top1_prob) {
+  long ticket = -1;
+  int rc = mnv1_forward_submit(ctx, images, n, logits, top1, top1_prob, &ticket);
+  if (rc) return rc;
+  return mnv1_forward_wait(ctx, ticket);
 }
 
 int mnv1_forward_upto(mnv1_ctx* ctx, const uint8_t* images, int n, int last_layer, float* host_nchw) {
@@ -795,6 +870,7 @@ int mnv1_forward_upto(mnv1_ctx* ctx, const uint8_t* images, int n, int last_laye
   if (rc) return rc;
   if (!images || !host_nchw || last_layer < 1 || last_layer > MNV1_NUM_LAYERS)
     return fail(ctx, MNV1_EINVAL, "forward_upto: bad arguments");
+  for (auto& sl : ctx->slots) if ((rc = finish_slot(ctx, sl)) != MNV1_OK) return rc;
   CK(ctx, cudaMemcpyAsync(ctx->d_images, images, (size_t)n * kImgBytes, cudaMemcpyHostToDevice, ctx->stream));
   const void* res = nullptr;
   CK(ctx, enqueue_layers(ctx, ctx->d_images, n, last_layer, ctx->d_logits, ctx->d_top1, ctx->d_prob, &res, nullptr));

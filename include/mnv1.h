@@ -145,6 +145,13 @@ int mnv1_plan(mnv1_ctx* ctx, int max_batch);
  * top1 [n], top1_prob [n] — any output may be NULL.  Includes H2D, the 28 launches, D2H. */
 int mnv1_forward(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int* top1,
                  float* top1_prob);
+/* the same, split so that consecutive batches overlap: submit enqueues H2D (copy stream), the
+ * graph (context stream) and D2H (third stream) and returns; wait blocks until that batch's
+ * outputs are in the caller's arrays.  Two batches may be in flight; submitting a third first
+ * retires the oldest.  Page-locked caller buffers (mnv1_host_alloc) are copied from / to directly. */
+int mnv1_forward_submit(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int* top1,
+                        float* top1_prob, long* ticket);
+int mnv1_forward_wait(mnv1_ctx* ctx, long ticket);
 /* device in, device out, asynchronous on the context stream (no copies, no sync) */
 int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images_u8, int n, void* d_logits_f32,
                         void* d_top1_i32, void* d_top1_prob_f32);

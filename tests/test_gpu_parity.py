@@ -317,3 +317,39 @@ def test_errors_and_empty(mn):
         c.forward(np.zeros((1, 224, 224, 3), np.uint8))  # no weights
     assert e.value.code == -5
     c.close()
+
+
+def test_pipelined_forward_matches_blocking(mn, synth_net):
+    """mnv1_forward_submit/_wait with two batches in flight returns the same bits as mnv1_forward,
+    for pinned (torch) and pageable (numpy) caller buffers."""
+    import torch
+    from mnv1_b200 import synth
+    c = _net_ctx(mn, mn.BF16, synth_net)
+    n = 32
+    batches = [synth.images(n, first=k * n) for k in range(4)]
+    want = [c.forward(b) for b in batches]
+    outs = []
+    prev = None
+    for k, b in enumerate(batches):
+        pinned = k % 2 == 0
+        if pinned:
+            hi = torch.from_numpy(b.copy()).pin_memory()
+            lg = torch.empty(n, 1000).pin_memory(); t1 = torch.empty(n, dtype=torch.int32).pin_memory()
+            p1 = torch.empty(n).pin_memory()
+            ptrs = (hi.data_ptr(), lg.data_ptr(), t1.data_ptr(), p1.data_ptr())
+            outs.append((hi, lg, t1, p1))
+        else:
+            hi = np.ascontiguousarray(b); lg = np.empty((n, 1000), np.float32); t1 = np.empty(n, np.int32)
+            p1 = np.empty(n, np.float32)
+            ptrs = (hi.ctypes.data, lg.ctypes.data, t1.ctypes.data, p1.ctypes.data)
+            outs.append((hi, lg, t1, p1))
+        t = c.forward_submit(ptrs[0], n, ptrs[1], ptrs[2], ptrs[3])
+        if prev is not None:
+            c.forward_wait(prev)
+        prev = t
+    c.forward_wait(prev)
+    for (hi, lg, t1, p1), (wl, wt, wp) in zip(outs, want):
+        lg = lg.numpy() if hasattr(lg, "numpy") and not isinstance(lg, np.ndarray) else lg
+        t1 = t1.numpy() if not isinstance(t1, np.ndarray) else t1
+        assert np.array_equal(lg, wl) and np.array_equal(t1, wt)
+    c.close()
