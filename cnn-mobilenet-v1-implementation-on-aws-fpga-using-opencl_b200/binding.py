@@ -15,7 +15,7 @@ import numpy as np
 from .layers import LAYERS, NUM_CLASSES, TOTAL_CHANNELS, TOTAL_WEIGHTS
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libmnv1.so")
+LIB_PATH = os.environ.get("MNV1_LIB", os.path.join(PKG_DIR, "libmnv1.so"))  # MNV1_LIB: kernel experiments only
 HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "mnv1.h")
 
 F32, BF16 = 0, 1

@@ -305,12 +305,14 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory");
+#ifndef PW_EXP_NOSTORE
         if (leader) {
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_out),
                        "r"(sbuf), "r"(n_idx + c0), "r"(m_idx)
                        : "memory");
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+#endif
       }
       tc_fence_before();
       __syncwarp();

@@ -97,7 +97,9 @@ struct StemTcParams {
   long m_total;
 };
 
-template <int S, bool RELU>
+// IL: the image is the interleaved RGB payload (pix_stride 3), so the 9 bytes of a window row are
+// contiguous and every tap is [row pointer + immediate]; otherwise three separate planes.
+template <int S, bool RELU, bool IL>
 __global__ void __launch_bounds__(ST_THREADS, 4)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const StemTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -185,34 +187,58 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const StemTcParams 
     }
   };
 
-  int i = 0;
-  long prev_tile = -1;
-  for (long t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
-    const int buf = i & 1;
-    // ---- gather the 27 taps of pixel m into row `tid` of A[buf]
+  // ---- gather, split in two so that the 27 byte loads of tile i+1 are in flight while the
+  // epilogue of tile i-1 runs: issue_loads() only issues LDGs, finish_tile() converts and stores.
+  uint32_t tap[28];
+  bool have = false, interior = false;
+  int g_iy0 = 0, g_ix0 = 0;
+  const uint8_t* g_base[3] = {nullptr, nullptr, nullptr};
+  auto issue_loads = [&](long t) {
     const long m = t * 128 + tid;
+    have = m < p.m_total;
+    interior = false;
+    if (!have) return;
+    const int img = (int)(m / HoWo);
+    const int rem = (int)(m - (long)img * HoWo);
+    const int oy = rem / Wo, ox = rem - oy * Wo;
+    g_iy0 = oy * S - p.pad_lo; g_ix0 = ox * S - p.pad_lo;
+    g_base[0] = p.r + (long)img * p.img_stride; g_base[1] = p.g + (long)img * p.img_stride;
+    g_base[2] = p.b + (long)img * p.img_stride;
+    interior = g_iy0 >= 0 && g_ix0 >= 0 && g_iy0 + 2 < H && g_ix0 + 2 < W;
+    if (!interior) return;
+    if (IL) {
+      const uint8_t* r0 = g_base[0] + ((long)g_iy0 * W + g_ix0) * 3;
+      const uint8_t* r1 = r0 + (long)W * 3;
+      const uint8_t* r2 = r1 + (long)W * 3;
+#pragma unroll
+      for (int jj = 0; jj < 3; ++jj)
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) {
+          tap[pl * 9 + 0 + jj] = __ldg(r0 + jj * 3 + pl);
+          tap[pl * 9 + 3 + jj] = __ldg(r1 + jj * 3 + pl);
+          tap[pl * 9 + 6 + jj] = __ldg(r2 + jj * 3 + pl);
+        }
+    } else {
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        const uint8_t* r0 = g_base[pl] + (long)g_iy0 * W + g_ix0;
+        const uint8_t* r1 = r0 + W;
+        const uint8_t* r2 = r1 + W;
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) {
+          tap[pl * 9 + 0 + jj] = __ldg(r0 + jj);
+          tap[pl * 9 + 3 + jj] = __ldg(r1 + jj);
+          tap[pl * 9 + 6 + jj] = __ldg(r2 + jj);
+        }
+      }
+    }
+  };
+  auto finish_tile = [&](int buf) {
     uint32_t a[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) a[q] = 0u;
-    if (m < p.m_total) {
-      const int img = (int)(m / HoWo);
-      const int rem = (int)(m - (long)img * HoWo);
-      const int oy = rem / Wo, ox = rem - oy * Wo;
-      const int iy0 = oy * S - p.pad_lo, ix0 = ox * S - p.pad_lo;
-      const uint8_t* planes[3] = {p.r + (long)img * p.img_stride, p.g + (long)img * p.img_stride,
-                                  p.b + (long)img * p.img_stride};
-      const bool interior = iy0 >= 0 && ix0 >= 0 && iy0 + 2 < H && ix0 + 2 < W;
-      uint32_t tap[28];
-      tap[27] = 0;
+    if (have) {
       if (interior) {
-#pragma unroll
-        for (int pl = 0; pl < 3; ++pl) {
-          const uint8_t* base = planes[pl] + ((long)iy0 * W + ix0) * ps;
-#pragma unroll
-          for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) tap[pl * 9 + ii * 3 + jj] = __ldg(base + ((long)ii * W + jj) * ps);
-        }
 #pragma unroll
         for (int q = 0; q < 13; ++q) a[q] = u8x2_to_f16x2(tap[2 * q], tap[2 * q + 1]);
         a[13] = u8x2_to_f16x2(tap[26], 0u) & 0x0000ffffu;
@@ -226,10 +252,10 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const StemTcParams 
           for (int ii = 0; ii < 3; ++ii)
 #pragma unroll
             for (int jj = 0; jj < 3; ++jj) {
-              const int y = iy0 + ii, x = ix0 + jj;
+              const int y = g_iy0 + ii, x = g_ix0 + jj;
               unsigned short h = padv;
               if (y >= 0 && y < H && x >= 0 && x < W)
-                h = __half_as_ushort(__ushort2half_rn((unsigned short)__ldg(planes[pl] + ((long)y * W + x) * ps)));
+                h = __half_as_ushort(__ushort2half_rn((unsigned short)__ldg(g_base[pl] + ((long)y * W + x) * ps)));
               hv[pl * 9 + ii * 3 + jj] = h;
             }
         hv[27] = 0;
@@ -237,11 +263,17 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const StemTcParams 
         for (int q = 0; q < 14; ++q) a[q] = (uint32_t)hv[2 * q] | ((uint32_t)hv[2 * q + 1] << 16);
       }
     }
-    {
-      const uint32_t arow = sA + buf * ST_A_BYTES + tid * 128;
+    const uint32_t arow = sA + buf * ST_A_BYTES + tid * 128;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) sts128(arow + ((c ^ (tid & 7)) << 4), a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
-    }
+    for (int c = 0; c < 4; ++c) sts128(arow + ((c ^ (tid & 7)) << 4), a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+  };
+
+  int i = 0;
+  long prev_tile = -1;
+  if ((long)blockIdx.x < tiles) issue_loads(blockIdx.x);
+  for (long t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+    const int buf = i & 1;
+    finish_tile(buf);                                   // taps of tile t were issued one iteration ago
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // staging buffer reuse
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -254,6 +286,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const StemTcParams 
       umma_f16(tmem_d, descA + 2, descB + 2, 1u);    // k = 16..31
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * buf) : "memory");
     }
+    if (t + gridDim.x < tiles) issue_loads(t + gridDim.x);   // next tile's loads fly during the epilogue
     if (i > 0) epilogue(prev_tile, i - 1);
     prev_tile = t;
   }
@@ -344,12 +377,21 @@ cudaError_t launch_stem_tc(bf16* out, const StemArgs& a, const __half* wq_dev, c
   if (!attr_set) {
     cudaError_t e = cudaSuccess;
     auto set = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
-    set((const void*)stem_tc_kernel<1, true>); set((const void*)stem_tc_kernel<1, false>);
-    set((const void*)stem_tc_kernel<2, true>); set((const void*)stem_tc_kernel<2, false>);
+    set((const void*)stem_tc_kernel<1, true, true>); set((const void*)stem_tc_kernel<1, false, true>);
+    set((const void*)stem_tc_kernel<2, true, true>); set((const void*)stem_tc_kernel<2, false, true>);
+    set((const void*)stem_tc_kernel<1, true, false>); set((const void*)stem_tc_kernel<1, false, false>);
+    set((const void*)stem_tc_kernel<2, true, false>); set((const void*)stem_tc_kernel<2, false, false>);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-#define ST_LAUNCH(S, R) stem_tc_kernel<S, R><<<(unsigned)grid, ST_THREADS, smem, st>>>(tm, p)
+  // interleaved = one base pointer with g = r + 1, b = r + 2 and pixel stride 3
+  const bool il = a.pix_stride == 3 && a.g == a.r + 1 && a.b == a.r + 2;
+  if (!il && a.pix_stride != 1) return cudaErrorNotSupported;
+#define ST_LAUNCH(S, R)                                                                          \
+  do {                                                                                            \
+    if (il) stem_tc_kernel<S, R, true><<<(unsigned)grid, ST_THREADS, smem, st>>>(tm, p);          \
+    else    stem_tc_kernel<S, R, false><<<(unsigned)grid, ST_THREADS, smem, st>>>(tm, p);         \
+  } while (0)
   if (a.stride == 2) { if (relu) ST_LAUNCH(2, true); else ST_LAUNCH(2, false); }
   else               { if (relu) ST_LAUNCH(1, true); else ST_LAUNCH(1, false); }
 #undef ST_LAUNCH
