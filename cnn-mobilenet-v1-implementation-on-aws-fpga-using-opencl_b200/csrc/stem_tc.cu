@@ -24,7 +24,7 @@
 namespace mnv1 {
 namespace {
 
-constexpr int ST_THREADS = 128;
+constexpr int ST_THREADS = 288;   // 4 gather warps + 4 epilogue warps + 1 MMA/TMEM warp
 constexpr int ST_C = 32;
 constexpr uint32_t ST_A_BYTES = 128 * 128;   // 128 pixels x 128-byte swizzle rows (first 64 B = 32 fp16 used)
 constexpr uint32_t ST_B_BYTES = 32 * 128;
@@ -41,12 +41,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "ST_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra ST_DONE;\n"
       "bra ST_WAIT;\n"
       "ST_DONE:\n"
       "}\n" ::"r"(bar),
-      "r"(parity), "r"(20000u)
+      "r"(parity)
       : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -99,40 +99,47 @@ struct StemTcParams {
 
 // IL: the image is the interleaved RGB payload (pix_stride 3), so the 9 bytes of a window row are
 // contiguous and every tap is [row pointer + immediate]; otherwise three separate planes.
+//
+// Warp roles (288 threads): warps 0-3 gather (thread g builds row g of the A tile), warps 4-7
+// epilogue (warp 4+q owns TMEM lanes 32q..), warp 8 = TMEM allocator + MMA issuer.  Two A tiles,
+// two accumulators and two staging buffers; mbarriers a_full[2] (128 gather arrivals),
+// mma_done[2] (tcgen05.commit: "D ready" for the epilogue AND "A free" for the gatherers),
+// tmem_free[2] (4 epilogue-warp arrivals).  Gather of tile i+1, MMA of tile i and epilogue of
+// tile i-1 therefore run concurrently instead of back to back.
 template <int S, bool RELU, bool IL>
-__global__ void __launch_bounds__(ST_THREADS, 4)
+__global__ void __launch_bounds__(ST_THREADS, 3)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const StemTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem;                         // 2 x 16 KB
   const uint32_t sB = smem + 2 * ST_A_BYTES;        // 4 KB
   const uint32_t sO = sB + ST_B_BYTES;              // 2 x 8 KB
-  const uint32_t bar0 = sO + 2 * ST_O_BYTES;        // mma_done[2]
-  const uint32_t tmem_slot = bar0 + 16;
-  __shared__ float s_scale[ST_C], s_shift[ST_C];
+  const uint32_t bars = sO + 2 * ST_O_BYTES;        // a_full[2] | mma_done[2] | tmem_free[2]
+  const uint32_t tmem_slot = bars + 48;
+  __shared__ __align__(16) float s_scale[ST_C];
+  __shared__ __align__(16) float s_shift[ST_C];
+  const uint32_t a_full = bars, mma_done = bars + 16, tmem_free = bars + 32;
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < ST_C) {
     s_scale[tid] = p.scale ? p.scale[tid] : 1.f;
     s_shift[tid] = p.shift2[tid];
-  }
-  if (tid == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
-    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  // B tile: thread t < 32 writes filter row t (32 fp16 = 4 chunks) with the 128B swizzle
-  if (tid < ST_C) {
+    // B tile: thread t < 32 writes filter row t (32 fp16 = 4 chunks) with the 128B swizzle
     const uint4* src = reinterpret_cast<const uint4*>(p.wq + tid * 32);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const uint4 v = __ldg(src + c);
       sts128(sB + tid * 128 + ((c ^ (tid & 7)) << 4), v.x, v.y, v.z, v.w);
     }
+  }
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_out) : "memory");
+    for (int b = 0; b < 2; ++b) { mbar_init(a_full + 8 * b, 128); mbar_init(mma_done + 8 * b, 1); mbar_init(tmem_free + 8 * b, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -142,159 +149,171 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const StemTcParams 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   const int Wo = p.ocols, HoWo = p.orows * p.ocols, W = p.cols, H = p.rows, ps = p.pix_stride;
-  const uint64_t descB = make_smem_desc(sB);
   const long tiles = (p.m_total + 127) / 128;
 
-  // epilogue of tile j (runs one iteration late so the MMA round trip is hidden behind a gather)
-  auto epilogue = [&](long j_tile, int j) {
-    const int buf = j & 1;
-    mbar_wait(bar0 + 8 * buf, (uint32_t)(j >> 1) & 1u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t v[32];
-    {
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * ST_C);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    }
-    const uint32_t orow = sO + buf * ST_O_BYTES + tid * 64;
+  if (warp < 4) {
+    // ======================= gather warps =======================
+    int i = 0;
+    for (long t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+      const int buf = i & 1, k = i >> 1;
+      const long m = t * 128 + tid;
+      uint32_t a[16];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint32_t pk[4];
+      for (int q = 0; q < 16; ++q) a[q] = 0u;
+      if (m < p.m_total) {
+        // 32-bit index math (m_total < 2^31 is checked on the host): a 64-bit divide is a subroutine
+        const unsigned mu = (unsigned)m;
+        const int img = (int)(mu / (unsigned)HoWo);
+        const int rem = (int)(mu - (unsigned)img * (unsigned)HoWo);
+        const int oy = (int)((unsigned)rem / (unsigned)Wo), ox = rem - oy * Wo;
+        const int iy0 = oy * S - p.pad_lo, ix0 = ox * S - p.pad_lo;
+        const uint8_t* base[3] = {p.r + (long)img * p.img_stride, p.g + (long)img * p.img_stride,
+                                  p.b + (long)img * p.img_stride};
+        if (iy0 >= 0 && ix0 >= 0 && iy0 + 2 < H && ix0 + 2 < W) {
+          uint32_t tap[28];
+          tap[27] = 0;
+#ifdef ST_EXP_NOLOAD
+          for (int q = 0; q < 27; ++q) tap[q] = (tid + q) & 255;
+          if (false) {
+#else
+          if (IL) {
+#endif
+            const uint8_t* r0 = base[0] + ((long)iy0 * W + ix0) * 3;
+            const uint8_t* r1 = r0 + (long)W * 3;
+            const uint8_t* r2 = r1 + (long)W * 3;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int ch = c * 8 + e * 2;
-        pk[e] = pack2<RELU>(fmaf(__uint_as_float(v[ch]), s_scale[ch], s_shift[ch]),
-                            fmaf(__uint_as_float(v[ch + 1]), s_scale[ch + 1], s_shift[ch + 1]), p.cap2);
-      }
-      sts128(orow + ((c ^ ((tid >> 1) & 3)) << 4), pk[0], pk[1], pk[2], pk[3]);   // SWIZZLE_64B
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_out),
-                   "r"(sO + buf * ST_O_BYTES), "r"(0), "r"((int)(j_tile * 128))
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-  };
-
-  // ---- gather, split in two so that the 27 byte loads of tile i+1 are in flight while the
-  // epilogue of tile i-1 runs: issue_loads() only issues LDGs, finish_tile() converts and stores.
-  uint32_t tap[28];
-  bool have = false, interior = false;
-  int g_iy0 = 0, g_ix0 = 0;
-  const uint8_t* g_base[3] = {nullptr, nullptr, nullptr};
-  auto issue_loads = [&](long t) {
-    const long m = t * 128 + tid;
-    have = m < p.m_total;
-    interior = false;
-    if (!have) return;
-    const int img = (int)(m / HoWo);
-    const int rem = (int)(m - (long)img * HoWo);
-    const int oy = rem / Wo, ox = rem - oy * Wo;
-    g_iy0 = oy * S - p.pad_lo; g_ix0 = ox * S - p.pad_lo;
-    g_base[0] = p.r + (long)img * p.img_stride; g_base[1] = p.g + (long)img * p.img_stride;
-    g_base[2] = p.b + (long)img * p.img_stride;
-    interior = g_iy0 >= 0 && g_ix0 >= 0 && g_iy0 + 2 < H && g_ix0 + 2 < W;
-    if (!interior) return;
-    if (IL) {
-      const uint8_t* r0 = g_base[0] + ((long)g_iy0 * W + g_ix0) * 3;
-      const uint8_t* r1 = r0 + (long)W * 3;
-      const uint8_t* r2 = r1 + (long)W * 3;
+            for (int jj = 0; jj < 3; ++jj)
 #pragma unroll
-      for (int jj = 0; jj < 3; ++jj)
+              for (int pl = 0; pl < 3; ++pl) {
+                tap[pl * 9 + 0 + jj] = __ldg(r0 + jj * 3 + pl);
+                tap[pl * 9 + 3 + jj] = __ldg(r1 + jj * 3 + pl);
+                tap[pl * 9 + 6 + jj] = __ldg(r2 + jj * 3 + pl);
+              }
+          } else {
 #pragma unroll
-        for (int pl = 0; pl < 3; ++pl) {
-          tap[pl * 9 + 0 + jj] = __ldg(r0 + jj * 3 + pl);
-          tap[pl * 9 + 3 + jj] = __ldg(r1 + jj * 3 + pl);
-          tap[pl * 9 + 6 + jj] = __ldg(r2 + jj * 3 + pl);
-        }
-    } else {
+            for (int pl = 0; pl < 3; ++pl) {
+              const uint8_t* r0 = base[pl] + (long)iy0 * W + ix0;
+              const uint8_t* r1 = r0 + W;
+              const uint8_t* r2 = r1 + W;
 #pragma unroll
-      for (int pl = 0; pl < 3; ++pl) {
-        const uint8_t* r0 = g_base[pl] + (long)g_iy0 * W + g_ix0;
-        const uint8_t* r1 = r0 + W;
-        const uint8_t* r2 = r1 + W;
-#pragma unroll
-        for (int jj = 0; jj < 3; ++jj) {
-          tap[pl * 9 + 0 + jj] = __ldg(r0 + jj);
-          tap[pl * 9 + 3 + jj] = __ldg(r1 + jj);
-          tap[pl * 9 + 6 + jj] = __ldg(r2 + jj);
-        }
-      }
-    }
-  };
-  auto finish_tile = [&](int buf) {
-    uint32_t a[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) a[q] = 0u;
-    if (have) {
-      if (interior) {
-#pragma unroll
-        for (int q = 0; q < 13; ++q) a[q] = u8x2_to_f16x2(tap[2 * q], tap[2 * q + 1]);
-        a[13] = u8x2_to_f16x2(tap[26], 0u) & 0x0000ffffu;
-      } else {
-        // border pixel: out-of-range taps read p0 (the raw value whose transform is zero)
-        unsigned short hv[28];
-        const unsigned short padv = (unsigned short)(p.pad_f16x2 & 0xffffu);
-#pragma unroll
-        for (int pl = 0; pl < 3; ++pl)
-#pragma unroll
-          for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 3; ++jj) {
-              const int y = g_iy0 + ii, x = g_ix0 + jj;
-              unsigned short h = padv;
-              if (y >= 0 && y < H && x >= 0 && x < W)
-                h = __half_as_ushort(__ushort2half_rn((unsigned short)__ldg(g_base[pl] + ((long)y * W + x) * ps)));
-              hv[pl * 9 + ii * 3 + jj] = h;
+              for (int jj = 0; jj < 3; ++jj) {
+                tap[pl * 9 + 0 + jj] = __ldg(r0 + jj);
+                tap[pl * 9 + 3 + jj] = __ldg(r1 + jj);
+                tap[pl * 9 + 6 + jj] = __ldg(r2 + jj);
+              }
             }
-        hv[27] = 0;
+          }
 #pragma unroll
-        for (int q = 0; q < 14; ++q) a[q] = (uint32_t)hv[2 * q] | ((uint32_t)hv[2 * q + 1] << 16);
+          for (int q = 0; q < 14; ++q) a[q] = u8x2_to_f16x2(tap[2 * q], tap[2 * q + 1]);
+          a[13] &= 0x0000ffffu;
+        } else {
+          // border pixel: out-of-range taps read p0 (the raw value whose transform is zero)
+          unsigned short hv[28];
+          const unsigned short padv = (unsigned short)(p.pad_f16x2 & 0xffffu);
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl)
+#pragma unroll
+            for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+              for (int jj = 0; jj < 3; ++jj) {
+                const int y = iy0 + ii, x = ix0 + jj;
+                unsigned short h = padv;
+                if (y >= 0 && y < H && x >= 0 && x < W)
+                  h = __half_as_ushort(__ushort2half_rn((unsigned short)__ldg(base[pl] + ((long)y * W + x) * ps)));
+                hv[pl * 9 + ii * 3 + jj] = h;
+              }
+          hv[27] = 0;
+#pragma unroll
+          for (int q = 0; q < 14; ++q) a[q] = (uint32_t)hv[2 * q] | ((uint32_t)hv[2 * q + 1] << 16);
+        }
       }
-    }
-    const uint32_t arow = sA + buf * ST_A_BYTES + tid * 128;
+      // A[buf] was last read by the MMAs of tile i-2: wait for their commit before overwriting
+      if (k > 0) mbar_wait(mma_done + 8 * buf, (uint32_t)(k - 1) & 1u);
+      const uint32_t arow = sA + buf * ST_A_BYTES + tid * 128;
+#ifndef ST_EXP_NOGATHERSTS
 #pragma unroll
-    for (int c = 0; c < 4; ++c) sts128(arow + ((c ^ (tid & 7)) << 4), a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
-  };
-
-  int i = 0;
-  long prev_tile = -1;
-  if ((long)blockIdx.x < tiles) issue_loads(blockIdx.x);
-  for (long t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
-    const int buf = i & 1;
-    finish_tile(buf);                                   // taps of tile t were issued one iteration ago
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // staging buffer reuse
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
+      for (int c = 0; c < 4; ++c) sts128(arow + ((c ^ (tid & 7)) << 4), a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#else
+      if (a[0] == 0x12345678u) sts128(arow, a[0], a[1], a[2], a[3]);
+#endif
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a_full + 8 * buf) : "memory");
+    }
+  } else if (warp < 8) {
+    // ======================= epilogue warps =======================
+    const int q = warp & 3, row = q * 32 + lane;       // TMEM lane quarter q, tile row
+    const bool leader = tid == 128;
+    int i = 0;
+    for (long t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+      const int buf = i & 1, k = i >> 1;
+      mbar_wait(mma_done + 8 * buf, (uint32_t)k & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[32];
+      {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * ST_C);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_free + 8 * buf) : "memory");
+#ifdef ST_EXP_NOEPI
+      if (v[0] == 0x12345678u) p.shift2 ? (void)0 : (void)0;
+      continue;
+#endif
+      // staging buffer `buf` was read by the TMA store of tile i-2
+      if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const uint32_t orow = sO + buf * ST_O_BYTES + row * 64;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 s0 = *reinterpret_cast<const float4*>(&s_scale[c * 8]), s1 = *reinterpret_cast<const float4*>(&s_scale[c * 8 + 4]);
+        const float4 t0 = *reinterpret_cast<const float4*>(&s_shift[c * 8]), t1 = *reinterpret_cast<const float4*>(&s_shift[c * 8 + 4]);
+        const uint32_t p0 = pack2<RELU>(fmaf(__uint_as_float(v[c * 8 + 0]), s0.x, t0.x), fmaf(__uint_as_float(v[c * 8 + 1]), s0.y, t0.y), p.cap2);
+        const uint32_t p1 = pack2<RELU>(fmaf(__uint_as_float(v[c * 8 + 2]), s0.z, t0.z), fmaf(__uint_as_float(v[c * 8 + 3]), s0.w, t0.w), p.cap2);
+        const uint32_t p2 = pack2<RELU>(fmaf(__uint_as_float(v[c * 8 + 4]), s1.x, t1.x), fmaf(__uint_as_float(v[c * 8 + 5]), s1.y, t1.y), p.cap2);
+        const uint32_t p3 = pack2<RELU>(fmaf(__uint_as_float(v[c * 8 + 6]), s1.z, t1.z), fmaf(__uint_as_float(v[c * 8 + 7]), s1.w, t1.w), p.cap2);
+        sts128(orow + ((c ^ ((row >> 1) & 3)) << 4), p0, p1, p2, p3);   // SWIZZLE_64B
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+#ifndef ST_EXP_NOSTORE
+      if (leader) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmap_out),
+                     "r"(sO + buf * ST_O_BYTES), "r"(0), "r"((int)(t * 128))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+#endif
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (lane == 0) {
+    // ======================= MMA issuer =======================
+    const uint64_t descB = make_smem_desc(sB);
+    int i = 0;
+    for (long t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+      const int buf = i & 1, k = i >> 1;
+      if (k > 0) mbar_wait(tmem_free + 8 * buf, (uint32_t)(k - 1) & 1u);   // accumulator drained by the epilogue
+      mbar_wait(a_full + 8 * buf, (uint32_t)k & 1u);                        // A tile written
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint64_t descA = make_smem_desc(sA + buf * ST_A_BYTES);
       const uint32_t tmem_d = tmem_base + (uint32_t)(buf * ST_C);
       umma_f16(tmem_d, descA, descB, 0u);            // k = 0..15
       umma_f16(tmem_d, descA + 2, descB + 2, 1u);    // k = 16..31
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar0 + 8 * buf) : "memory");
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mma_done + 8 * buf) : "memory");
     }
-    if (t + gridDim.x < tiles) issue_loads(t + gridDim.x);   // next tile's loads fly during the epilogue
-    if (i > 0) epilogue(prev_tile, i - 1);
-    prev_tile = t;
   }
-  if (i > 0) epilogue(prev_tile, i - 1);
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
   }
@@ -347,6 +366,7 @@ cudaError_t launch_stem_tc(bf16* out, const StemArgs& a, const __half* wq_dev, c
                            std::string* err) {
   if (a.cout != ST_C || (a.stride != 1 && a.stride != 2)) return cudaErrorNotSupported;
   if (a.n <= 0) return cudaSuccess;
+  if ((long)a.n * (a.rows / a.stride) * (a.cols / a.stride) >= (1L << 31)) return cudaErrorNotSupported;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) { if (err) *err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
   StemTcParams p{};
@@ -370,7 +390,7 @@ cudaError_t launch_stem_tc(bf16* out, const StemArgs& a, const __half* wq_dev, c
   }
   const size_t smem = 1024 + 2 * ST_A_BYTES + ST_B_BYTES + 2 * ST_O_BYTES + 64;
   const long tiles = (p.m_total + 127) / 128;
-  long grid = (long)num_sms * 4;
+  long grid = (long)num_sms * 3;
   if (grid > tiles) grid = tiles;
   const bool relu = act != MNV1_ACT_NONE;
   static bool attr_set = false;
