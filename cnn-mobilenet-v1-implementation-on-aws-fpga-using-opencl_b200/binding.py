@@ -214,6 +214,12 @@ class Context:
         fn = lib().mnv1_pointwise_simt if simt else lib().mnv1_pointwise
         self._ck(fn(self.h, out.h, inp.h, f.h, rows, cols, filtersize, op_size))
 
+    def dw_pw_block(self, out: Buffer, inp: Buffer, dw: Filter, pw: Filter, rows, cols, stride):
+        self._ck(lib().mnv1_dw_pw_block(self.h, out.h, inp.h, dw.h, pw.h, rows, cols, stride))
+
+    def use_fused_blocks(self, on: bool):
+        self._ck(lib().mnv1_ctx_use_fused_blocks(self.h, int(on)))
+
     def pool(self, out: Buffer, inp: Buffer, rows, cols, filtersize, op_size):
         self._ck(lib().mnv1_pool(self.h, out.h, inp.h, rows, cols, filtersize, op_size))
 

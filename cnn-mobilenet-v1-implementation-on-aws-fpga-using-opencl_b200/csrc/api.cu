@@ -94,8 +94,10 @@ struct mnv1_ctx {
   } slots[2];
   cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
   long next_ticket = 0;
+  long graph_kernels = 30;
   std::map<GraphKey, cudaGraphExec_t> graphs;
   bool use_graph = true;
+  bool use_fused = true;   // depthwise->pointwise block fusion inside mnv1_forward*
 };
 
 static int fail(mnv1_ctx* ctx, int code, const std::string& msg) {
@@ -712,6 +714,21 @@ static cudaError_t enqueue_layers(mnv1_ctx* ctx, const uint8_t* d_img, int n, in
         cur = dst; side ^= 1;
         break;
       case MNV1_DEPTHWISE:
+        // depthwise + the pointwise that follows as one kernel where a fused variant exists: the
+        // depthwise map then never leaves the SM
+        if (ctx->use_fused && ctx->dtype == MNV1_BF16 && i + 1 < last && L[i + 1].kind == MNV1_POINTWISE) {
+          ctx->err.clear();
+          cudaError_t fe = mnv1::launch_fused_dw_pw((bf16*)dst, (const bf16*)cur, f, ctx->net[i + 1], n, L[i].hin, L[i].hin,
+                                                    L[i].stride, ctx->num_sms, ctx->stream, &ctx->err);
+          if (fe != cudaErrorNotSupported) {
+            e = fe;
+            ctx->launches++; ctx->last_kernel = "fused_dw_pw_kernel";
+            cur = dst; side ^= 1;
+            ++i;  // the pointwise layer is done too
+            if (evs) cudaEventRecord(evs[i], ctx->stream);
+            break;
+          }
+        }
         e = run_depthwise(ctx, dst, cur, f, n, L[i].hin, L[i].hin, L[i].stride);
         cur = dst; side ^= 1;
         break;
@@ -774,7 +791,8 @@ int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images, int n, void* d_logi
     cudaError_t e = enqueue_layers(ctx, (const uint8_t*)d_images, n, MNV1_NUM_LAYERS, (float*)d_logits, (int*)d_top1,
                                    (float*)d_prob, nullptr, nullptr);
     cudaError_t e2 = cudaStreamEndCapture(ctx->stream, &graph);
-    ctx->launches = before;  // capture enqueues nothing
+    ctx->graph_kernels = ctx->launches - before;  // kernels per replay
+    ctx->launches = before;                        // capture enqueues nothing
     if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail_cuda(ctx, e, "graph capture (layer launch)"); }
     if (e2 != cudaSuccess) return fail_cuda(ctx, e2, "cudaStreamEndCapture");
     cudaGraphExec_t exec = nullptr;
@@ -784,7 +802,38 @@ int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images, int n, void* d_logi
     it = ctx->graphs.emplace(key, exec).first;
   }
   CK(ctx, cudaGraphLaunch(it->second, ctx->stream));
-  ctx->launches += 27 + ((d_top1 || d_prob) ? 3 : 2);
+  ctx->launches += ctx->graph_kernels;
+  return MNV1_OK;
+}
+
+int mnv1_ctx_use_fused_blocks(mnv1_ctx* ctx, int on) {
+  if (!ctx) return MNV1_EINVAL;
+  ctx->use_fused = on != 0;
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  ctx->graphs.clear();
+  return MNV1_OK;
+}
+
+// one depthwise(3x3) + pointwise(1x1) block through the fused kernel (MNV1_EUNSUPPORTED when the
+// shape has no fused variant): out [n][cout][rows/stride][cols/stride]
+int mnv1_dw_pw_block(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* dw, const mnv1_filter* pw,
+                     int rows, int cols, int stride) {
+  if (!ctx || !out || !in || !dw || !pw) return fail(ctx, MNV1_EINVAL, "dw_pw_block: null argument");
+  if (dw->kind != MNV1_DEPTHWISE || pw->kind != MNV1_POINTWISE || pw->cin != dw->cout)
+    return fail(ctx, MNV1_EINVAL, "dw_pw_block: filter mismatch");
+  if (ctx->dtype != MNV1_BF16) return fail(ctx, MNV1_EUNSUPPORTED, "dw_pw_block: bf16 contexts only");
+  int rc = check_fmap(ctx, in, dw->cout, rows, cols, "dw_pw_block(in)");
+  if (rc) return rc;
+  rc = check_fmap(ctx, out, pw->cout, rows / stride, cols / stride, "dw_pw_block(out)");
+  if (rc) return rc;
+  if (in->n != out->n) return fail(ctx, MNV1_EINVAL, "dw_pw_block: batch mismatch");
+  TimedLaunch tl(ctx);
+  ctx->err.clear();
+  cudaError_t e = mnv1::launch_fused_dw_pw((bf16*)out->d, (const bf16*)in->d, dw, pw, in->n, rows, cols, stride,
+                                           ctx->num_sms, ctx->stream, &ctx->err);
+  if (e == cudaErrorNotSupported) return fail(ctx, MNV1_EUNSUPPORTED, "dw_pw_block: no fused variant for this shape");
+  ctx->launches++; ctx->last_kernel = "fused_dw_pw_kernel";
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "dw_pw_block");
   return MNV1_OK;
 }
 

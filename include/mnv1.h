@@ -172,6 +172,12 @@ const char* mnv1_last_kernel_name(const mnv1_ctx* ctx);
  * cross-check the tcgen05 kernel on the device.  Same arguments as mnv1_pointwise. */
 int mnv1_pointwise_simt(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* filter,
                         int rows, int cols, int filtersize, int op_size);
+/* depthwise(3x3) -> pointwise(1x1) as one kernel: the depthwise map stays in shared memory as the
+ * GEMM's A operand (bf16 contexts; MNV1_EUNSUPPORTED when the shape has no fused variant).
+ * mnv1_forward* uses it automatically; mnv1_ctx_use_fused_blocks(ctx, 0) turns that off. */
+int mnv1_dw_pw_block(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* dw_filter,
+                     const mnv1_filter* pw_filter, int rows, int cols, int stride);
+int mnv1_ctx_use_fused_blocks(mnv1_ctx* ctx, int on);
 /* 1 (default): mnv1_forward* replays a captured CUDA graph; 0: launches the kernels eagerly */
 int mnv1_ctx_use_graph(mnv1_ctx* ctx, int on);
 /* page-locked host memory (CL_MEM_ALLOC_HOST_PTR analogue): mnv1_forward copies straight
