@@ -10,13 +10,14 @@
 //
 // Work item = (image, band of R output rows): M tile = R*W pixels (98 of 128 rows used at 14x14),
 // all Cin channels in 64-wide k-blocks, all Cout (<= 512) channels as one or two 256-column
-// accumulators in TMEM.  18 warps:
+// accumulators in TMEM.  20 warps:
 //   warp 0        TMA producer: depthwise input halo tiles [R+2][W+2][64] (4-D map, OOB = padding)
 //                 and filter tiles [256][64] into two mbarrier rings
 //   warp 1        TMEM allocator + tcgen05.mma issuer
-//   warps 2-9     stencil: thread = (4 channels, 1 column); input-row-major accumulation into a
-//                 3-row ring (as depthwise_tma.cu), BN shift/ReLU6, pack, st.shared into A[k-block]
-//   warps 10-17   epilogue: tcgen05.ld -> fma(scale, shift) -> ReLU/cap -> swizzled staging -> TMA store
+//   warps 2-15    stencil (the pace-setter, so it gets most of the SM): warp = one column, lane =
+//                 2 channels; input-row-major accumulation into a 3-row ring (as depthwise_tma.cu),
+//                 BN shift/ReLU6, pack, st.shared into A[k-block]
+//   warps 16-19   epilogue: tcgen05.ld -> fma(scale, shift) -> ReLU/cap -> swizzled staging -> TMA store
 #include <cstdio>
 
 #include "common.cuh"
@@ -24,8 +25,8 @@
 namespace mnv1 {
 namespace {
 
-constexpr int FB_THREADS = 18 * 32;
-constexpr int FB_DW_WARPS = 8, FB_EPI_WARPS = 8;
+constexpr int FB_DW_WARPS = 14, FB_EPI_WARPS = 4;
+constexpr int FB_THREADS = (2 + FB_DW_WARPS + FB_EPI_WARPS) * 32;
 constexpr uint32_t FB_A_BYTES = 128 * 128;        // 128 rows x 64 bf16
 constexpr uint32_t FB_B_BYTES = 256 * 128;        // 256 filters x 64 bf16
 constexpr uint32_t FB_O_BYTES = 128 * 128;
@@ -82,18 +83,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ uint2 lds64(uint32_t addr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b) {
-  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds64f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t a) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -125,7 +131,7 @@ fused_dw_pw_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   constexpr int HR = R + 2, HW = W + 2;                       // halo tile
   constexpr uint32_t IN_BYTES = (uint32_t)HR * HW * 64 * 2;
   constexpr uint32_t IN_PITCH = (IN_BYTES + 1023u) & ~1023u;
-  static_assert(R * W <= 128 && W <= 16, "item does not fit one UMMA M tile / the stencil threads");
+  static_assert(R * W <= 128 && W <= FB_DW_WARPS, "item does not fit one UMMA M tile / the stencil warps");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -226,55 +232,51 @@ fused_dw_pw_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
     }
   } else if (warp < 2 + FB_DW_WARPS) {
     // ======================= stencil warps =======================
-    const int d = tid - 64;
-    const int cq = d & 15, col = d >> 4;                  // 4-channel quad, column
+    const int col = warp - 2;                             // one column per warp
+    const int cp = lane;                                  // channel pair inside the 64-wide k-block
     const bool active = col < W;
     const int colc = active ? col : 0;
     int is = 0; uint32_t iph = 0; int as = 0; uint32_t aph = 0;
     for (long it = blockIdx.x; it < p.items; it += gridDim.x) {
       for (int kb = 0; kb < num_kb; ++kb) {
-        // this k-block's taps and shift for the thread's 4 channels
-        float w[9][4], sh[4];
-        const uint32_t tap0 = sTaps + (uint32_t)(kb * 64 + cq * 4) * 4u;
+        // this k-block's taps and shift for the thread's 2 channels
+        float w[9][2], sh[2];
+        const uint32_t tap0 = sTaps + (uint32_t)(kb * 64 + cp * 2) * 4u;
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-          const float4 a = lds128f(tap0 + (uint32_t)k * C * 4u);
-          w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+          const float2 a = lds64f(tap0 + (uint32_t)k * C * 4u);
+          w[k][0] = a.x; w[k][1] = a.y;
         }
         {
-          const float4 a = lds128f(sDwShift + (uint32_t)(kb * 64 + cq * 4) * 4u);
-          sh[0] = a.x; sh[1] = a.y; sh[2] = a.z; sh[3] = a.w;
+          const float2 a = lds64f(sDwShift + (uint32_t)(kb * 64 + cp * 2) * 4u);
+          sh[0] = a.x; sh[1] = a.y;
         }
         mbar_wait(in_full + 8 * is, iph);                 // halo tile landed
         mbar_wait(a_empty + 8 * as, aph ^ 1u);            // A tile no longer read by the MMAs
-        const uint32_t src = sIn + is * IN_PITCH + (uint32_t)(colc * 64 + cq * 4) * 2u;
-        const uint32_t dstA = sA + as * FB_A_BYTES;
-        float acc[3][4];
+        const uint32_t src = sIn + is * IN_PITCH + (uint32_t)(colc * 64 + cp * 2) * 2u;
+        const uint32_t dstA = sA + as * FB_A_BYTES + ((uint32_t)(cp & 3) << 2);
+        float acc[3][2];
 #pragma unroll
-        for (int a = 0; a < 3; ++a)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[a][v] = 0.f;
+        for (int a = 0; a < 3; ++a) acc[a][0] = acc[a][1] = 0.f;
 #pragma unroll
         for (int q = 0; q < HR; ++q) {                    // input row q of the halo tile
-          float x[3][4];
+          float x[3][2];
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
-            const uint2 raw = lds64(src + (uint32_t)((q * HW + j) * 64 * 2));
-            x[j][0] = bf16lo_to_f32(raw.x); x[j][1] = bf16hi_to_f32(raw.x);
-            x[j][2] = bf16lo_to_f32(raw.y); x[j][3] = bf16hi_to_f32(raw.y);
+            const uint32_t raw = lds32(src + (uint32_t)((q * HW + j) * 64 * 2));
+            x[j][0] = bf16lo_to_f32(raw); x[j][1] = bf16hi_to_f32(raw);
           }
           const int a0 = q % 3, a1 = (q + 2) % 3, a2 = (q + 1) % 3;   // output rows q, q-1, q-2
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
+          for (int v = 0; v < 2; ++v) {
             acc[a0][v] = fmaf(x[2][v], w[2][v], fmaf(x[1][v], w[1][v], fmaf(x[0][v], w[0][v], sh[v])));
             acc[a1][v] = fmaf(x[2][v], w[5][v], fmaf(x[1][v], w[4][v], fmaf(x[0][v], w[3][v], acc[a1][v])));
             acc[a2][v] = fmaf(x[2][v], w[8][v], fmaf(x[1][v], w[7][v], fmaf(x[0][v], w[6][v], acc[a2][v])));
           }
           if (q >= 2 && active) {                         // output row q-2 is complete
             const int pix = (q - 2) * W + col;            // row of the A tile
-            const uint32_t lo = pack2<DW_RELU>(acc[a2][0], acc[a2][1], p.dw_cap2);
-            const uint32_t hi = pack2<DW_RELU>(acc[a2][2], acc[a2][3], p.dw_cap2);
-            sts64(dstA + (uint32_t)pix * 128u + ((uint32_t)((cq >> 1) ^ (pix & 7)) << 4) + (uint32_t)(cq & 1) * 8u, lo, hi);
+            sts32(dstA + (uint32_t)pix * 128u + ((uint32_t)((cp >> 2) ^ (pix & 7)) << 4),
+                  pack2<DW_RELU>(acc[a2][0], acc[a2][1], p.dw_cap2));
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -287,7 +289,7 @@ fused_dw_pw_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
   } else {
     // ======================= epilogue warps =======================
     const int ew = warp - (2 + FB_DW_WARPS);
-    const int quarter = warp & 3, half = ew >> 2;          // TMEM lane quarter (warp % 4), 32-column half
+    const int quarter = warp & 3;                          // TMEM lane quarter = warp % 4
     const int row = quarter * 32 + lane;
     const bool leader = ew == 0 && lane == 0;
     const uint32_t row_off = (uint32_t)row * 128u, row_x = (uint32_t)(row & 7);
@@ -303,31 +305,34 @@ fused_dw_pw_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_con
         const uint32_t sbuf = sO + (blk & 1u) * FB_O_BYTES;
         if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(32 * FB_EPI_WARPS) : "memory");
-        uint32_t v[32];
-        {
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 64 + 32 * half);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        }
-        const uint32_t colb = (uint32_t)(b * 64 + 32 * half);
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          const float4 s0 = lds128f(sPwScale + (colb + j) * 4u), s1 = lds128f(sPwScale + (colb + j + 4) * 4u);
-          const float4 t0 = lds128f(sPwShift + (colb + j) * 4u), t1 = lds128f(sPwShift + (colb + j + 4) * 4u);
-          const uint32_t q0 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 0]), s0.x, t0.x), fmaf(__uint_as_float(v[j + 1]), s0.y, t0.y), p.pw_cap2);
-          const uint32_t q1 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 2]), s0.z, t0.z), fmaf(__uint_as_float(v[j + 3]), s0.w, t0.w), p.pw_cap2);
-          const uint32_t q2 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 4]), s1.x, t1.x), fmaf(__uint_as_float(v[j + 5]), s1.y, t1.y), p.pw_cap2);
-          const uint32_t q3 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 6]), s1.z, t1.z), fmaf(__uint_as_float(v[j + 7]), s1.w, t1.w), p.pw_cap2);
-          const uint32_t chunk = (uint32_t)(4 * half + j / 8);
-          sts128(sbuf + row_off + ((chunk ^ row_x) << 4), q0, q1, q2, q3);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          {
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 64 + 32 * half);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
+          const uint32_t colb = (uint32_t)(b * 64 + 32 * half);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const float4 s0 = lds128f(sPwScale + (colb + j) * 4u), s1 = lds128f(sPwScale + (colb + j + 4) * 4u);
+            const float4 t0 = lds128f(sPwShift + (colb + j) * 4u), t1 = lds128f(sPwShift + (colb + j + 4) * 4u);
+            const uint32_t q0 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 0]), s0.x, t0.x), fmaf(__uint_as_float(v[j + 1]), s0.y, t0.y), p.pw_cap2);
+            const uint32_t q1 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 2]), s0.z, t0.z), fmaf(__uint_as_float(v[j + 3]), s0.w, t0.w), p.pw_cap2);
+            const uint32_t q2 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 4]), s1.x, t1.x), fmaf(__uint_as_float(v[j + 5]), s1.y, t1.y), p.pw_cap2);
+            const uint32_t q3 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 6]), s1.z, t1.z), fmaf(__uint_as_float(v[j + 7]), s1.w, t1.w), p.pw_cap2);
+            const uint32_t chunk = (uint32_t)(4 * half + j / 8);
+            sts128(sbuf + row_off + ((chunk ^ row_x) << 4), q0, q1, q2, q3);
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, %0;" ::"n"(32 * FB_EPI_WARPS) : "memory");
