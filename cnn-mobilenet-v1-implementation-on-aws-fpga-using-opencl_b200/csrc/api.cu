@@ -719,7 +719,8 @@ static cudaError_t enqueue_layers(mnv1_ctx* ctx, const uint8_t* d_img, int n, in
         if (ctx->use_fused && ctx->dtype == MNV1_BF16 && i + 1 < last && L[i + 1].kind == MNV1_POINTWISE) {
           ctx->err.clear();
           cudaError_t fe = mnv1::launch_fused_dw_pw((bf16*)dst, (const bf16*)cur, f, ctx->net[i + 1], n, L[i].hin, L[i].hin,
-                                                    L[i].stride, ctx->num_sms, ctx->stream, &ctx->err);
+                                                    L[i].stride, pad_lo_for(ctx, L[i].stride), ctx->num_sms, ctx->stream,
+                                                    &ctx->err);
           if (fe != cudaErrorNotSupported) {
             e = fe;
             ctx->launches++; ctx->last_kernel = "fused_dw_pw_kernel";
@@ -830,7 +831,7 @@ int mnv1_dw_pw_block(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv
   TimedLaunch tl(ctx);
   ctx->err.clear();
   cudaError_t e = mnv1::launch_fused_dw_pw((bf16*)out->d, (const bf16*)in->d, dw, pw, in->n, rows, cols, stride,
-                                           ctx->num_sms, ctx->stream, &ctx->err);
+                                           pad_lo_for(ctx, stride), ctx->num_sms, ctx->stream, &ctx->err);
   if (e == cudaErrorNotSupported) return fail(ctx, MNV1_EUNSUPPORTED, "dw_pw_block: no fused variant for this shape");
   ctx->launches++; ctx->last_kernel = "fused_dw_pw_kernel";
   if (e != cudaSuccess) return fail_cuda(ctx, e, "dw_pw_block");

@@ -19,6 +19,7 @@
 //                 BN shift/ReLU6, pack, st.shared into A[k-block]
 //   warps 16-19   epilogue: tcgen05.ld -> fma(scale, shift) -> ReLU/cap -> swizzled staging -> TMA store
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -434,7 +435,14 @@ cudaError_t launch_fb(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
 
 // cudaErrorNotSupported (nothing launched) when the block shape has no fused variant.
 cudaError_t launch_fused_dw_pw(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n,
-                               int rows, int cols, int stride, int num_sms, cudaStream_t st, std::string* err) {
+                               int rows, int cols, int stride, int pad_lo, int num_sms, cudaStream_t st,
+                               std::string* err) {
+  {  // blocks whose pointwise filter stays resident in shared memory (layers 2-11)
+    cudaError_t e = launch_fused_rb(out, in, dw, pw, n, rows, cols, stride, pad_lo, num_sms, st, err);
+    if (e != cudaErrorNotSupported) return e;
+  }
+  static const bool fb_on = !getenv("MNV1_NO_FB");   // debug switch for the 14x14 variant
+  if (!fb_on) return cudaErrorNotSupported;
   if (stride != 1 || !dw->w_scaled || !pw->has_tmap || pw->tmap_bn != 256 || pw->cin != dw->cout) return cudaErrorNotSupported;
   if (dw->cout % 64 || pw->cout % 256 || pw->cout > 512 || dw->cout > 1024) return cudaErrorNotSupported;
   if (n <= 0) return cudaSuccess;

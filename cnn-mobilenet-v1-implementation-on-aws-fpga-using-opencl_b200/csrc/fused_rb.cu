@@ -1,0 +1,441 @@
+// fused_rb.cu — depthwise 3x3 (stride 1 or 2) + pointwise 1x1 as ONE kernel, for the blocks whose
+// pointwise filter fits in shared memory (layers 2-11 of the MobileNet.c schedule).
+//
+// Replaces a `depthwise` launch (kernel.cl:62-92) and the `pointwise` launch that follows it
+// (kernel.cl:94-114) in mnv1_forward*: the depthwise map — 45 % of the activation traffic of those
+// layers — is never written to HBM.  Arithmetic is the same as depthwise_tma.cu
+// followed by pointwise_tc.cu (fp32 stencil in the same tap order, bf16 rounding of the depthwise
+// value, bf16 x bf16 -> fp32 UMMA), so the results are bit-identical to the two-kernel path.
+//
+// A tile is R x TWO output pixels (<= 128, one UMMA M tile; TMEM lane = r*TP + x, TP = 16).  A unit
+// is (tile, 64-channel k-block).  One persistent CTA per SM:
+//   warp 0        TMA producer: the whole pointwise filter once (it stays resident), then the
+//                 depthwise input as halo row-chunks [RC][(TWO-1)*S+3][CK] of each unit through a 4-D
+//                 tensor map (out-of-bounds = the layer's zero padding) into a ring of NI stages
+//   warp 1        TMEM allocator + single-thread tcgen05.mma issuer: D[128 x Cout] (+)= A_unit . B_kb^T
+//   warps 2-5     epilogue: tcgen05.ld -> fma(scale, shift) -> ReLU/cap -> swizzled staging -> 4-D TMA store
+//   warps 6..     NG stencil groups of 4 warps; group g owns units g, g+NG, ...: a thread keeps 4
+//                 channels x TW columns, walks the halo rows once (ld.shared.v2, widen once), keeps a
+//                 ring of 3 (S=1) / 2 (S=2) output-row accumulators, and writes each finished row as
+//                 bf16 straight into the 128B-swizzled K-major A operand of its unit.
+// Every group has a private ring of NIG chunk stages (consecutive uses of a stage are waited on by the
+// same warps, which is what makes the parity wait safe: TMA completions are not ordered, so a group
+// sharing stages with the others could run two phases ahead of a barrier).  The producer fills the
+// rings in "wavefront" order (chunk k of the NG units of a round, then chunk k+1 ...).
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace mnv1 {
+namespace {
+
+using namespace ptx;
+
+constexpr int RB_GW = 4;          // warps per stencil group
+constexpr int RB_EPI_WARPS = 4;   // one per TMEM lane quarter
+constexpr int RB_TP = 16;         // TMEM-lane pitch of a tile row
+constexpr uint32_t RB_A_BYTES = 128 * 128;   // A tile: 128 rows x 64 bf16, 128B swizzle
+constexpr uint32_t RB_O_BYTES = 128 * 128;   // output staging block: 128 rows x 64 bf16
+
+// S stride; CK channels per k-block; NKB k-blocks (C = CK*NKB); COUT; tile = R x TWO outputs;
+// TW output columns per stencil thread; RC input rows per chunk; NG stencil groups; NIG chunk stages
+// per group; NA A-tile stages (a multiple of NG: a stage always belongs to one group); NSTG output
+// staging buffers.
+template <int S_, int CK_, int NKB_, int COUT_, int TWO_, int R_, int TW_, int RC_, int NG_, int NIG_, int NA_, int NSTG_>
+struct RbCfg {
+  static constexpr int S = S_, CK = CK_, NKB = NKB_, COUT = COUT_, TWO = TWO_, R = R_, TW = TW_, RC = RC_;
+  static constexpr int NG = NG_, NIG = NIG_, NI = NG_ * NIG_, NA = NA_, NSTG = NSTG_;
+  static constexpr int C = CK * NKB;
+  static constexpr int HR = (R - 1) * S + 3;          // input rows per tile
+  static constexpr int BW = (TWO - 1) * S + 3;        // input columns per tile
+  static constexpr int NCHK = (HR + RC - 1) / RC;     // chunks per unit
+  static constexpr int CQ = CK / 4;                   // channel quads per pixel
+  static constexpr int PG = TWO / TW;                 // column groups
+  static constexpr int NCOL = (TW - 1) * S + 3;       // input columns a thread reads per row
+  static constexpr int RING = S == 1 ? 3 : 2;
+  static constexpr uint32_t LINE = CK * 2;            // bytes per pixel in a chunk
+  static constexpr uint32_t CHUNK_BYTES = (uint32_t)RC * BW * LINE;
+  static constexpr uint32_t CHUNK_PITCH = (CHUNK_BYTES + 127u) & ~127u;
+  static constexpr uint32_t B_BYTES = (uint32_t)COUT * 128;   // one k-block of the filter
+  static constexpr int WARPS = 2 + RB_EPI_WARPS + NG * RB_GW;
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr int NBAR = 2 * NI + 2 * NA + 4 + 1;
+  static constexpr uint32_t OFF_B = 0;
+  static constexpr uint32_t OFF_A = OFF_B + NKB * B_BYTES;
+  static constexpr uint32_t OFF_O = OFF_A + NA * RB_A_BYTES;
+  static constexpr uint32_t OFF_IN = OFF_O + NSTG * RB_O_BYTES;
+  static constexpr uint32_t OFF_TAPS = OFF_IN + NI * CHUNK_PITCH;
+  static constexpr uint32_t OFF_DSH = OFF_TAPS + 9u * C * 4;
+  static constexpr uint32_t OFF_PSC = OFF_DSH + (uint32_t)C * 4;
+  static constexpr uint32_t OFF_PSH = OFF_PSC + (uint32_t)COUT * 4;
+  static constexpr uint32_t OFF_BAR = OFF_PSH + (uint32_t)COUT * 4;
+  static constexpr uint32_t OFF_END = OFF_BAR + 8u * NBAR + 16;
+  static constexpr size_t SMEM = 1024 + OFF_END;
+  static_assert(R * RB_TP <= 128 && TWO <= RB_TP, "tile does not fit one UMMA M tile");
+  static_assert(TWO % TW == 0 && PG * CQ <= RB_GW * 32, "tile does not fit a stencil group");
+  static_assert(CK == 32 || CK == 64, "k-block is 32 or 64 channels");
+  static_assert(COUT % 64 == 0 && COUT <= 256, "Cout: multiple of 64, at most 256 (two TMEM stages)");
+  static_assert(NA % NG == 0 && NIG >= 2, "A stages are owned by one group each; rings hold at least two chunks");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
+};
+
+struct RbParams {
+  const float* dw_taps;    // [9][C] taps x folded-BN scale
+  const float* dw_shift;   // [C] or nullptr
+  const float* pw_scale;   // [Cout] or nullptr
+  const float* pw_shift;   // [Cout] or nullptr
+  uint32_t dw_cap2, pw_cap2;
+  int bands, strips, pad_lo;
+  long tiles;              // n * bands * strips
+};
+
+template <class Cfg, bool DW_RELU, bool PW_RELU>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_b,
+                const __grid_constant__ CUtensorMap tmap_out, const RbParams p) {
+  constexpr int S = Cfg::S, CK = Cfg::CK, NKB = Cfg::NKB, COUT = Cfg::COUT, TWO = Cfg::TWO, R = Cfg::R, TW = Cfg::TW;
+  constexpr int RC = Cfg::RC, NG = Cfg::NG, NIG = Cfg::NIG, NI = Cfg::NI, NA = Cfg::NA, NSTG = Cfg::NSTG, C = Cfg::C;
+  constexpr int HR = Cfg::HR, BW = Cfg::BW, NCHK = Cfg::NCHK, CQ = Cfg::CQ, PG = Cfg::PG, NCOL = Cfg::NCOL;
+  constexpr int RING = Cfg::RING;
+  constexpr uint32_t LINE = Cfg::LINE;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem_g = smem_raw + (smem - smem_u32(smem_raw));   // generic view of the same base
+  const uint32_t sB = smem + Cfg::OFF_B, sA = smem + Cfg::OFF_A, sO = smem + Cfg::OFF_O, sIn = smem + Cfg::OFF_IN;
+  const uint32_t sTaps = smem + Cfg::OFF_TAPS, sDsh = smem + Cfg::OFF_DSH, sPsc = smem + Cfg::OFF_PSC, sPsh = smem + Cfg::OFF_PSH;
+  const uint32_t bars = smem + Cfg::OFF_BAR;
+  const uint32_t in_full = bars, in_empty = in_full + 8u * NI, a_full = in_empty + 8u * NI, a_empty = a_full + 8u * NA;
+  const uint32_t tm_full = a_empty + 8u * NA, tm_empty = tm_full + 16, b_full = tm_empty + 16, tmem_slot = b_full + 8;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // constants -> shared memory
+  {
+    float* taps = reinterpret_cast<float*>(smem_g + Cfg::OFF_TAPS);
+    for (int i = tid; i < 9 * C; i += Cfg::THREADS) taps[i] = p.dw_taps[i];
+    float* ds = reinterpret_cast<float*>(smem_g + Cfg::OFF_DSH);
+    for (int i = tid; i < C; i += Cfg::THREADS) ds[i] = p.dw_shift ? p.dw_shift[i] : 0.f;
+    float* ps = reinterpret_cast<float*>(smem_g + Cfg::OFF_PSC);
+    float* pt = reinterpret_cast<float*>(smem_g + Cfg::OFF_PSH);
+    for (int i = tid; i < COUT; i += Cfg::THREADS) { ps[i] = p.pw_scale ? p.pw_scale[i] : 1.f; pt[i] = p.pw_shift ? p.pw_shift[i] : 0.f; }
+  }
+  if (tid == 0) {
+    prefetch_tmap(&tmap_in); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_out);
+    for (int s = 0; s < NI; ++s) { mbar_init(in_full + 8u * s, 1); mbar_init(in_empty + 8u * s, RB_GW); }
+    for (int s = 0; s < NA; ++s) { mbar_init(a_full + 8u * s, RB_GW); mbar_init(a_empty + 8u * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tm_full + 8u * s, 1); mbar_init(tm_empty + 8u * s, RB_EPI_WARPS); }
+    mbar_init(b_full, 1);
+    mbar_init_fence();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = lds32(tmem_slot);
+
+  // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const long G = gridDim.x;
+  const int nt = (int)((p.tiles - blockIdx.x + G - 1) / G);     // > 0: the grid never exceeds the tile count
+  const int total_units = nt * NKB;
+  const int per_img = p.bands * p.strips;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      mbar_expect_tx(b_full, NKB * Cfg::B_BYTES);
+      for (int kb = 0; kb < NKB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmap_b, b_full, kb * 64, 0);
+      int stage[NG]; uint32_t phase[NG];                   // per-group ring position
+#pragma unroll
+      for (int g = 0; g < NG; ++g) { stage[g] = 0; phase[g] = 0; }
+      for (int u0 = 0; u0 < total_units; u0 += NG) {
+        const int nu = total_units - u0 < NG ? total_units - u0 : NG;
+        int cx[NG], cy[NG], cc[NG], ci[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          const int ul = u0 + (g < nu ? g : 0);
+          const int lt = ul / NKB, kb = ul - lt * NKB;
+          const long tile = blockIdx.x + (long)lt * G;
+          const int img = (int)(tile / per_img), rem = (int)(tile - (long)img * per_img);
+          const int band = rem / p.strips, strip = rem - band * p.strips;
+          cx[g] = strip * TWO * S - p.pad_lo; cy[g] = band * R * S - p.pad_lo; cc[g] = kb * CK; ci[g] = img;
+        }
+#pragma unroll 1
+        for (int k = 0; k < NCHK; ++k) {
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            if (g < nu) {
+              const uint32_t st = (uint32_t)(g * NIG + stage[g]);
+              mbar_wait(in_empty + 8u * st, phase[g] ^ 1u);
+              mbar_expect_tx(in_full + 8u * st, Cfg::CHUNK_BYTES);
+              tma_load_4d(sIn + st * Cfg::CHUNK_PITCH, &tmap_in, in_full + 8u * st, cc[g], cx[g], cy[g] + k * RC, ci[g]);
+              if (++stage[g] == NIG) { stage[g] = 0; phase[g] ^= 1u; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_m128(COUT);
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      int ul = 0;
+      for (int lt = 0; lt < nt; ++lt) {
+        const uint32_t acc = (uint32_t)(lt & 1);
+        mbar_wait(tm_empty + 8u * acc, (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 256u;
+#pragma unroll 1
+        for (int kb = 0; kb < NKB; ++kb, ++ul) {
+          const uint32_t st = (uint32_t)ul % NA, ph = ((uint32_t)ul / NA) & 1u;
+          mbar_wait(a_full + 8u * st, ph);
+          tc_fence_after();
+          const uint64_t da = umma_desc_sw128(sA + st * RB_A_BYTES);
+          const uint64_t db = umma_desc_sw128(sB + kb * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < CK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(a_empty + 8u * st);
+        }
+        umma_commit(tm_full + 8u * acc);
+      }
+    }
+  } else if (warp < 2 + RB_EPI_WARPS) {
+    // ======================= epilogue warps =======================
+    const int quarter = warp & 3;                          // TMEM lane quarter = warp % 4
+    const int m = quarter * 32 + lane;                     // TMEM lane = tile pixel r*TP + x
+    const int mr = m / RB_TP, mx = m % RB_TP;
+    const bool valid = mr < R && mx < TWO;
+    const int line = valid ? mr * TWO + mx : 0;            // row of the dense [R*TWO][64] staging block
+    const uint32_t line_off = (uint32_t)line * 128u, line_x = (uint32_t)(line & 7);
+    const bool leader = warp == 2 && lane == 0;
+    uint32_t blk = 0;
+    for (int lt = 0; lt < nt; ++lt) {
+      const long tile = blockIdx.x + (long)lt * G;
+      const int img = (int)(tile / per_img), rem = (int)(tile - (long)img * per_img);
+      const int band = rem / p.strips, strip = rem - band * p.strips;
+      const uint32_t acc = (uint32_t)(lt & 1);
+      mbar_wait(tm_full + 8u * acc, ((uint32_t)lt >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int b = 0; b < COUT / 64; ++b, ++blk) {
+        const uint32_t sbuf = sO + (NSTG == 1 ? 0u : (blk % NSTG) * RB_O_BYTES);
+        if (leader) tma_store_wait_read<NSTG - 1>();         // the store that last read this buffer is done with it
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * RB_EPI_WARPS) : "memory");
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t v[32];
+          tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256u + (uint32_t)(b * 64 + 32 * half), v);
+          tmem_ld_wait();
+          const uint32_t colb = (uint32_t)(b * 64 + 32 * half);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const float4 s0 = lds128f(sPsc + (colb + j) * 4u), s1 = lds128f(sPsc + (colb + j + 4) * 4u);
+            const float4 t0 = lds128f(sPsh + (colb + j) * 4u), t1 = lds128f(sPsh + (colb + j + 4) * 4u);
+            const uint32_t q0 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 0]), s0.x, t0.x), fmaf(__uint_as_float(v[j + 1]), s0.y, t0.y), p.pw_cap2);
+            const uint32_t q1 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 2]), s0.z, t0.z), fmaf(__uint_as_float(v[j + 3]), s0.w, t0.w), p.pw_cap2);
+            const uint32_t q2 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 4]), s1.x, t1.x), fmaf(__uint_as_float(v[j + 5]), s1.y, t1.y), p.pw_cap2);
+            const uint32_t q3 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 6]), s1.z, t1.z), fmaf(__uint_as_float(v[j + 7]), s1.w, t1.w), p.pw_cap2);
+            const uint32_t chunk = (uint32_t)(4 * half + j / 8);
+            if (valid) sts128(sbuf + line_off + ((chunk ^ line_x) << 4), q0, q1, q2, q3);
+          }
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * RB_EPI_WARPS) : "memory");
+        if (leader) {
+          // box = 64 channels x TWO columns x R rows of one image; smem = dense [R*TWO][64], 128B swizzle
+          tma_store_4d(&tmap_out, sbuf, b * 64, strip * TWO, band * R, img);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tm_empty + 8u * acc);
+    }
+    if (leader) tma_store_wait_all();
+  } else {
+    // ======================= stencil groups =======================
+    const int g = (warp - (2 + RB_EPI_WARPS)) / RB_GW;
+    const int t = tid - (2 + RB_EPI_WARPS + g * RB_GW) * 32;    // 0..127 inside the group
+    const bool active = t < PG * CQ;
+    const int quad = t % CQ;
+    const int pg = active ? t / CQ : PG - 1;
+    // byte offset of the thread's first input column / channel quad inside a chunk
+    const uint32_t in_off = (uint32_t)(pg * TW * S) * LINE + (uint32_t)quad * 8u;
+    // A operand: row = r*TP + x (128 B each), 16-byte chunk XOR (row & 7) -- TP % 8 == 0, so the
+    // swizzle term depends on the column only
+    uint32_t a_off[TW];
+#pragma unroll
+    for (int c = 0; c < TW; ++c) {
+      const uint32_t x = (uint32_t)(pg * TW + c);
+      a_off[c] = x * 128u + ((((uint32_t)quad >> 1) ^ (x & 7u)) << 4) + ((uint32_t)quad & 1u) * 8u;
+    }
+    float w[9][4], sh[4];
+    auto load_taps = [&](int kb) {
+      const uint32_t ch = (uint32_t)(kb * CK + quad * 4) * 4u;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const float4 a = lds128f(sTaps + (uint32_t)k * C * 4u + ch);
+        w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+      }
+      const float4 a = lds128f(sDsh + ch);
+      sh[0] = a.x; sh[1] = a.y; sh[2] = a.z; sh[3] = a.w;
+    };
+    if (NKB == 1) load_taps(0);
+    uint32_t rstage = 0, rphase = 0;                      // position in the group's private chunk ring
+
+    for (int u0 = 0; u0 < total_units; u0 += NG) {
+      const int nu = total_units - u0 < NG ? total_units - u0 : NG;
+      if (g >= nu) break;
+      const int ul = u0 + g;
+      if (NKB > 1) load_taps(ul % NKB);
+      const uint32_t ast = (uint32_t)ul % NA, aph = ((uint32_t)ul / NA) & 1u;
+      const uint32_t dstA = sA + ast * RB_A_BYTES;
+
+      float acc[RING][TW][4];
+      uint32_t rowbase = 0, cur_stage = 0;
+#pragma unroll
+      for (int q = 0; q < HR; ++q) {
+        if (q % RC == 0) {                                  // next chunk of the unit
+          cur_stage = (uint32_t)(g * NIG) + rstage;
+          mbar_wait(in_full + 8u * cur_stage, rphase);
+          rowbase = sIn + cur_stage * Cfg::CHUNK_PITCH + in_off;
+          if (++rstage == NIG) { rstage = 0; rphase ^= 1u; }
+        }
+        float x[NCOL][4];
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+          const uint2 raw = lds64(rowbase + (uint32_t)(((q % RC) * BW + j) * LINE));
+          x[j][0] = bf16lo_to_f32(raw.x); x[j][1] = bf16hi_to_f32(raw.x);
+          x[j][2] = bf16lo_to_f32(raw.y); x[j][3] = bf16hi_to_f32(raw.y);
+        }
+        if (q % RC == RC - 1 || q == HR - 1) {              // chunk consumed: hand the stage back
+          __syncwarp();
+          if (lane == 0) mbar_arrive(in_empty + 8u * cur_stage);
+        }
+        // input row q feeds tap row tr of output row o = (q - tr) / S; tap rows accumulate in order
+        // 0, 1, 2 (the order of depthwise_tma.cu), the shift seeds the accumulator
+#pragma unroll
+        for (int tr = 2; tr >= 0; --tr) {
+          if ((q - tr) >= 0 && (q - tr) % S == 0 && (q - tr) / S < R) {
+            const int o = (q - tr) / S, slot = o % RING;
+#pragma unroll
+            for (int c = 0; c < TW; ++c)
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                const float init = tr == 0 ? sh[v] : acc[slot][c][v];
+                acc[slot][c][v] = fmaf(x[c * S + 2][v], w[3 * tr + 2][v],
+                                       fmaf(x[c * S + 1][v], w[3 * tr + 1][v], fmaf(x[c * S][v], w[3 * tr][v], init)));
+              }
+            if (tr == 2) {                                  // output row o is complete
+              if (o == 0) mbar_wait(a_empty + 8u * ast, aph ^ 1u);   // the MMAs that last read this A stage retired
+              if (active) {
+#pragma unroll
+                for (int c = 0; c < TW; ++c)
+                  sts64(dstA + a_off[c] + (uint32_t)(o * RB_TP) * 128u, pack2<DW_RELU>(acc[slot][c][0], acc[slot][c][1], p.dw_cap2),
+                        pack2<DW_RELU>(acc[slot][c][2], acc[slot][c][3], p.dw_cap2));
+              }
+            }
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full + 8u * ast);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+template <class Cfg>
+cudaError_t launch_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n, int H, int W,
+                      int pad_lo, int num_sms, cudaStream_t st, std::string* err) {
+  EncodeTiledFn fn = tensor_map_encoder();
+  if (!fn) { if (err) *err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
+  constexpr int S = Cfg::S, C = Cfg::C, COUT = Cfg::COUT;
+  const int Ho = H / S, Wo = W / S;
+  if (Ho % Cfg::R || Wo % Cfg::TWO) return cudaErrorNotSupported;
+  CUtensorMap tin, tout;
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)Cfg::CK, (cuuint32_t)Cfg::BW, (cuuint32_t)Cfg::RC, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&tin, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(in), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { if (err) *err = "fused block: input tensor map encode failed"; return cudaErrorInvalidValue; }
+  }
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)COUT, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)n};
+    cuuint64_t gstr[3] = {(cuuint64_t)COUT * 2, (cuuint64_t)Wo * COUT * 2, (cuuint64_t)Ho * Wo * COUT * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)Cfg::TWO, (cuuint32_t)Cfg::R, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { if (err) *err = "fused block: output tensor map encode failed"; return cudaErrorInvalidValue; }
+  }
+  RbParams p{};
+  p.dw_taps = dw->w_scaled; p.dw_shift = dw->shift; p.pw_scale = pw->scale; p.pw_shift = pw->shift;
+  p.dw_cap2 = dw->act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
+  p.pw_cap2 = pw->act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
+  p.bands = Ho / Cfg::R; p.strips = Wo / Cfg::TWO; p.pad_lo = pad_lo;
+  p.tiles = (long)n * p.bands * p.strips;
+  const bool dr = dw->act != MNV1_ACT_NONE, pr = pw->act != MNV1_ACT_NONE;
+  long grid = num_sms;
+  if (grid > p.tiles) grid = p.tiles;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaSuccess;
+    auto set = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM); };
+    set((const void*)fused_rb_kernel<Cfg, true, true>); set((const void*)fused_rb_kernel<Cfg, true, false>);
+    set((const void*)fused_rb_kernel<Cfg, false, true>); set((const void*)fused_rb_kernel<Cfg, false, false>);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+#define RB_LAUNCH(A, B) fused_rb_kernel<Cfg, A, B><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(tin, pw->tmap_b, tout, p)
+  if (dr) { if (pr) RB_LAUNCH(true, true); else RB_LAUNCH(true, false); }
+  else    { if (pr) RB_LAUNCH(false, true); else RB_LAUNCH(false, false); }
+#undef RB_LAUNCH
+  return cudaGetLastError();
+}
+
+//                   S  CK NKB COUT TWO R TW RC NG NIG NA NSTG
+using CfgL02 = RbCfg<1, 32, 1,  64, 16, 8, 1, 5, 3, 6, 3, 2>;   // 112x112x32  -> 112x112x64
+using CfgL04 = RbCfg<2, 64, 1, 128, 14, 8, 2, 2, 3, 5, 3, 2>;   // 112x112x64  -> 56x56x128
+using CfgL06 = RbCfg<1, 64, 2, 128, 14, 8, 2, 5, 3, 3, 3, 2>;   // 56x56x128   -> 56x56x128
+using CfgL08 = RbCfg<2, 64, 2, 256, 14, 7, 2, 2, 3, 4, 3, 1>;   // 56x56x128   -> 28x28x256
+using CfgL10 = RbCfg<1, 64, 4, 256, 14, 7, 2, 3, 2, 3, 2, 1>;   // 28x28x256   -> 28x28x256
+
+}  // namespace
+
+// cudaErrorNotSupported (nothing launched) when the block has no resident-filter variant.
+cudaError_t launch_fused_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n, int rows,
+                            int cols, int stride, int pad_lo, int num_sms, cudaStream_t st, std::string* err) {
+  if (!dw->w_scaled || !pw->has_tmap || pw->cin != dw->cout || pw->tmap_bn != pw->cout) return cudaErrorNotSupported;
+  if (n <= 0) return cudaSuccess;
+  const int c = dw->cout, co = pw->cout;
+  // MNV1_RB_MASK (debug): bit i enables the i-th variant below; default all
+  static const long mask = getenv("MNV1_RB_MASK") ? strtol(getenv("MNV1_RB_MASK"), nullptr, 0) : ~0L;
+#define RB_TRY(CFG, HW, BIT) \
+  if ((mask >> BIT & 1) && stride == CFG::S && c == CFG::C && co == CFG::COUT && rows == HW && cols == HW) \
+    return launch_rb<CFG>(out, in, dw, pw, n, rows, cols, pad_lo, num_sms, st, err)
+  RB_TRY(CfgL02, 112, 0);
+  RB_TRY(CfgL04, 112, 1);
+  RB_TRY(CfgL06, 56, 2);
+  RB_TRY(CfgL08, 56, 3);
+  RB_TRY(CfgL10, 28, 4);
+#undef RB_TRY
+  return cudaErrorNotSupported;
+}
+
+}  // namespace mnv1
