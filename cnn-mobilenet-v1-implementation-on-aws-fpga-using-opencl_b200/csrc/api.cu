@@ -366,6 +366,8 @@ int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, i
     case MNV1_POINTWISE:
     case MNV1_FC:           // [Cout][Cin] (kernel.cl:106) kept as is: it is the K-major B operand
       dev.assign(w, w + (size_t)cin * cout);
+      if (scale) f->h_scale.assign(scale, scale + cout);   // host copies: the fused block kernel takes them by value
+      if (shift) f->h_shift.assign(shift, shift + cout);
       break;
     default:
       return fail(ctx, MNV1_EINVAL, "filter kind has no weights");

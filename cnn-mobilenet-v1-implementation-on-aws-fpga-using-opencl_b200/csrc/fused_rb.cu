@@ -9,12 +9,14 @@
 //
 // A tile is R x TWO output pixels (<= 128, one UMMA M tile; TMEM lane = r*TP + x, TP = 16).  A unit
 // is (tile, 64-channel k-block).  One persistent CTA per SM:
-//   warp 0        TMA producer: the whole pointwise filter once (it stays resident), then the
+//   top warp      TMA producer: the whole pointwise filter once (it stays resident), then the
 //                 depthwise input as halo row-chunks [RC][(TWO-1)*S+3][CK] of each unit through a 4-D
 //                 tensor map (out-of-bounds = the layer's zero padding) into a ring of NI stages
-//   warp 1        TMEM allocator + single-thread tcgen05.mma issuer: D[128 x Cout] (+)= A_unit . B_kb^T
-//   warps 2-5     epilogue: tcgen05.ld -> fma(scale, shift) -> ReLU/cap -> swizzled staging -> 4-D TMA store
-//   warps 6..     NG stencil groups of 4 warps; group g owns units g, g+NG, ...: a thread keeps 4
+//   next          TMEM allocator + single-thread tcgen05.mma issuer: D[128 x Cout] (+)= A_unit . B_kb^T;
+//                 512 / Cout accumulator stages so the epilogue's latency never stalls the MMAs
+//   next 4        epilogue, each warp on its own (no barrier between them): tcgen05.ld of its 32 lanes
+//                 -> fma(scale, shift) -> ReLU/cap -> private swizzled staging -> one 4-D TMA store per tile row
+//   warps 0..     NG stencil groups of 4 warps; group g owns units g, g+NG, ...: a thread keeps 4
 //                 channels x TW columns, walks the halo rows once (ld.shared.v2, widen once), keeps a
 //                 ring of 3 (S=1) / 2 (S=2) output-row accumulators, and writes each finished row as
 //                 bf16 straight into the 128B-swizzled K-major A operand of its unit.
@@ -33,20 +35,19 @@ namespace {
 
 using namespace ptx;
 
-constexpr int RB_GW = 4;          // warps per stencil group
 constexpr int RB_EPI_WARPS = 4;   // one per TMEM lane quarter
 constexpr int RB_TP = 16;         // TMEM-lane pitch of a tile row
 constexpr uint32_t RB_A_BYTES = 128 * 128;   // A tile: 128 rows x 64 bf16, 128B swizzle
-constexpr uint32_t RB_O_BYTES = 128 * 128;   // output staging block: 128 rows x 64 bf16
+constexpr uint32_t RB_O_BYTES = 4 * 4096;    // output staging per buffer: 4 warps x 2 tile rows x (16 lines x 128 B)
 
 // S stride; CK channels per k-block; NKB k-blocks (C = CK*NKB); COUT; tile = R x TWO outputs;
-// TW output columns per stencil thread; RC input rows per chunk; NG stencil groups; NIG chunk stages
-// per group; NA A-tile stages (a multiple of NG: a stage always belongs to one group); NSTG output
-// staging buffers.
-template <int S_, int CK_, int NKB_, int COUT_, int TWO_, int R_, int TW_, int RC_, int NG_, int NIG_, int NA_, int NSTG_>
+// TW output columns per stencil thread; RC input rows per chunk; NG stencil groups of GW warps; NIG
+// chunk stages per group; NA A-tile stages (a multiple of NG: a stage always belongs to one group); NE
+// epilogue sets of 4 warps (set e takes tiles e, e+NE, ...); NSTG output staging buffers per warp.
+template <int S_, int CK_, int NKB_, int COUT_, int TWO_, int R_, int TW_, int RC_, int NG_, int GW_, int NIG_, int NA_, int NE_, int NSTG_>
 struct RbCfg {
   static constexpr int S = S_, CK = CK_, NKB = NKB_, COUT = COUT_, TWO = TWO_, R = R_, TW = TW_, RC = RC_;
-  static constexpr int NG = NG_, NIG = NIG_, NI = NG_ * NIG_, NA = NA_, NSTG = NSTG_;
+  static constexpr int NG = NG_, GW = GW_, NIG = NIG_, NI = NG_ * NIG_, NA = NA_, NE = NE_, NSTG = NSTG_;
   static constexpr int C = CK * NKB;
   static constexpr int HR = (R - 1) * S + 3;          // input rows per tile
   static constexpr int BW = (TWO - 1) * S + 3;        // input columns per tile
@@ -59,22 +60,21 @@ struct RbCfg {
   static constexpr uint32_t CHUNK_BYTES = (uint32_t)RC * BW * LINE;
   static constexpr uint32_t CHUNK_PITCH = (CHUNK_BYTES + 127u) & ~127u;
   static constexpr uint32_t B_BYTES = (uint32_t)COUT * 128;   // one k-block of the filter
-  static constexpr int WARPS = 2 + RB_EPI_WARPS + NG * RB_GW;
+  static constexpr int WARPS = 2 + NE * RB_EPI_WARPS + NG * GW;
   static constexpr int THREADS = WARPS * 32;
-  static constexpr int NBAR = 2 * NI + 2 * NA + 4 + 1;
+  static constexpr int NACC = 512 / COUT > 8 ? 8 : 512 / COUT;   // TMEM accumulator stages of COUT columns
+  static constexpr int NBAR = 2 * NI + 2 * NA + 2 * NACC + 1;
   static constexpr uint32_t OFF_B = 0;
   static constexpr uint32_t OFF_A = OFF_B + NKB * B_BYTES;
   static constexpr uint32_t OFF_O = OFF_A + NA * RB_A_BYTES;
-  static constexpr uint32_t OFF_IN = OFF_O + NSTG * RB_O_BYTES;
+  static constexpr uint32_t OFF_IN = OFF_O + NE * NSTG * RB_O_BYTES;
   static constexpr uint32_t OFF_TAPS = OFF_IN + NI * CHUNK_PITCH;
   static constexpr uint32_t OFF_DSH = OFF_TAPS + 9u * C * 4;
-  static constexpr uint32_t OFF_PSC = OFF_DSH + (uint32_t)C * 4;
-  static constexpr uint32_t OFF_PSH = OFF_PSC + (uint32_t)COUT * 4;
-  static constexpr uint32_t OFF_BAR = OFF_PSH + (uint32_t)COUT * 4;
+  static constexpr uint32_t OFF_BAR = OFF_DSH + (uint32_t)C * 4;
   static constexpr uint32_t OFF_END = OFF_BAR + 8u * NBAR + 16;
   static constexpr size_t SMEM = 1024 + OFF_END;
   static_assert(R * RB_TP <= 128 && TWO <= RB_TP, "tile does not fit one UMMA M tile");
-  static_assert(TWO % TW == 0 && PG * CQ <= RB_GW * 32, "tile does not fit a stencil group");
+  static_assert(TWO % TW == 0 && PG * CQ <= GW * 32, "tile does not fit a stencil group");
   static_assert(CK == 32 || CK == 64, "k-block is 32 or 64 channels");
   static_assert(COUT % 64 == 0 && COUT <= 256, "Cout: multiple of 64, at most 256 (two TMEM stages)");
   static_assert(NA % NG == 0 && NIG >= 2, "A stages are owned by one group each; rings hold at least two chunks");
@@ -84,33 +84,44 @@ struct RbCfg {
 struct RbParams {
   const float* dw_taps;    // [9][C] taps x folded-BN scale
   const float* dw_shift;   // [C] or nullptr
-  const float* pw_scale;   // [Cout] or nullptr
-  const float* pw_shift;   // [Cout] or nullptr
+  float pw_scale[256];     // folded-BN scale / shift of the pointwise layer, by value: they live in the
+  float pw_shift[256];     // kernel-parameter constant bank and feed the epilogue FFMAs as immediates
   uint32_t dw_cap2, pw_cap2;
   int bands, strips, pad_lo;
   long tiles;              // n * bands * strips
+  unsigned long long* trace;  // debug: per-event SM clock stamps of CTA 0 (MNV1_RB_TRACE), else nullptr
+  int dbg;                 // experiment switches (MNV1_RB_DBG): 2 no TMA store, 4 no epilogue math
 };
+
+// trace[role][idx][slot]: role 0 producer, 1 MMA, 2 epilogue, 3+g stencil group g; 128 entries x 4 stamps
+__device__ __forceinline__ void rb_stamp(unsigned long long* tr, int role, int idx, int slot) {
+  if (tr && blockIdx.x == 0 && idx < 128) tr[(role * 128 + idx) * 4 + slot] = clock64();
+}
 
 template <class Cfg, bool DW_RELU, bool PW_RELU>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_b,
-                const __grid_constant__ CUtensorMap tmap_out, const RbParams p) {
+                const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
+                const __grid_constant__ RbParams p) {
   constexpr int S = Cfg::S, CK = Cfg::CK, NKB = Cfg::NKB, COUT = Cfg::COUT, TWO = Cfg::TWO, R = Cfg::R, TW = Cfg::TW;
-  constexpr int RC = Cfg::RC, NG = Cfg::NG, NIG = Cfg::NIG, NI = Cfg::NI, NA = Cfg::NA, NSTG = Cfg::NSTG, C = Cfg::C;
+  constexpr int RC = Cfg::RC, NG = Cfg::NG, GW = Cfg::GW, NIG = Cfg::NIG, NI = Cfg::NI, NA = Cfg::NA, NE = Cfg::NE, NSTG = Cfg::NSTG, C = Cfg::C;
   constexpr int HR = Cfg::HR, BW = Cfg::BW, NCHK = Cfg::NCHK, CQ = Cfg::CQ, PG = Cfg::PG, NCOL = Cfg::NCOL;
-  constexpr int RING = Cfg::RING;
+  constexpr int RING = Cfg::RING, NACC = Cfg::NACC;
   constexpr uint32_t LINE = Cfg::LINE;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_g = smem_raw + (smem - smem_u32(smem_raw));   // generic view of the same base
   const uint32_t sB = smem + Cfg::OFF_B, sA = smem + Cfg::OFF_A, sO = smem + Cfg::OFF_O, sIn = smem + Cfg::OFF_IN;
-  const uint32_t sTaps = smem + Cfg::OFF_TAPS, sDsh = smem + Cfg::OFF_DSH, sPsc = smem + Cfg::OFF_PSC, sPsh = smem + Cfg::OFF_PSH;
+  const uint32_t sTaps = smem + Cfg::OFF_TAPS, sDsh = smem + Cfg::OFF_DSH;
   const uint32_t bars = smem + Cfg::OFF_BAR;
   const uint32_t in_full = bars, in_empty = in_full + 8u * NI, a_full = in_empty + 8u * NI, a_empty = a_full + 8u * NA;
-  const uint32_t tm_full = a_empty + 8u * NA, tm_empty = tm_full + 16, b_full = tm_empty + 16, tmem_slot = b_full + 8;
+  const uint32_t tm_full = a_empty + 8u * NA, tm_empty = tm_full + 8u * NACC, b_full = tm_empty + 8u * NACC, tmem_slot = b_full + 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // Warp roles.  The SM's issue arbiter favours the highest warp ids, so the latency-critical
+  // single-thread roles and the epilogue sit above the bulk stencil workers.
+  constexpr int W_EPI = NG * GW, W_MMA = W_EPI + NE * RB_EPI_WARPS, W_TMA = W_MMA + 1;
 
   // constants -> shared memory
   {
@@ -118,19 +129,16 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     for (int i = tid; i < 9 * C; i += Cfg::THREADS) taps[i] = p.dw_taps[i];
     float* ds = reinterpret_cast<float*>(smem_g + Cfg::OFF_DSH);
     for (int i = tid; i < C; i += Cfg::THREADS) ds[i] = p.dw_shift ? p.dw_shift[i] : 0.f;
-    float* ps = reinterpret_cast<float*>(smem_g + Cfg::OFF_PSC);
-    float* pt = reinterpret_cast<float*>(smem_g + Cfg::OFF_PSH);
-    for (int i = tid; i < COUT; i += Cfg::THREADS) { ps[i] = p.pw_scale ? p.pw_scale[i] : 1.f; pt[i] = p.pw_shift ? p.pw_shift[i] : 0.f; }
   }
   if (tid == 0) {
-    prefetch_tmap(&tmap_in); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_out);
-    for (int s = 0; s < NI; ++s) { mbar_init(in_full + 8u * s, 1); mbar_init(in_empty + 8u * s, RB_GW); }
-    for (int s = 0; s < NA; ++s) { mbar_init(a_full + 8u * s, RB_GW); mbar_init(a_empty + 8u * s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tm_full + 8u * s, 1); mbar_init(tm_empty + 8u * s, RB_EPI_WARPS); }
+    prefetch_tmap(&tmap_in); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_out); prefetch_tmap(&tmap_out2);
+    for (int s = 0; s < NI; ++s) { mbar_init(in_full + 8u * s, 1); mbar_init(in_empty + 8u * s, GW); }
+    for (int s = 0; s < NA; ++s) { mbar_init(a_full + 8u * s, GW); mbar_init(a_empty + 8u * s, 1); }
+    for (int s = 0; s < NACC; ++s) { mbar_init(tm_full + 8u * s, 1); mbar_init(tm_empty + 8u * s, RB_EPI_WARPS); }
     mbar_init(b_full, 1);
     mbar_init_fence();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512u);
+  if (warp == W_MMA) tmem_alloc(tmem_slot, 512u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -142,7 +150,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   const int total_units = nt * NKB;
   const int per_img = p.bands * p.strips;
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       mbar_expect_tx(b_full, NKB * Cfg::B_BYTES);
@@ -157,10 +165,10 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         for (int g = 0; g < NG; ++g) {
           const int ul = u0 + (g < nu ? g : 0);
           const int lt = ul / NKB, kb = ul - lt * NKB;
-          const long tile = blockIdx.x + (long)lt * G;
-          const int img = (int)(tile / per_img), rem = (int)(tile - (long)img * per_img);
-          const int band = rem / p.strips, strip = rem - band * p.strips;
-          cx[g] = strip * TWO * S - p.pad_lo; cy[g] = band * R * S - p.pad_lo; cc[g] = kb * CK; ci[g] = img;
+          const uint32_t tile = blockIdx.x + (uint32_t)lt * (uint32_t)G;
+          const uint32_t img = tile / (uint32_t)per_img, rem = tile - img * (uint32_t)per_img;
+          const uint32_t band = rem / (uint32_t)p.strips, strip = rem - band * (uint32_t)p.strips;
+          cx[g] = (int)strip * TWO * S - p.pad_lo; cy[g] = (int)band * R * S - p.pad_lo; cc[g] = kb * CK; ci[g] = (int)img;
         }
 #pragma unroll 1
         for (int k = 0; k < NCHK; ++k) {
@@ -171,13 +179,14 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
               mbar_wait(in_empty + 8u * st, phase[g] ^ 1u);
               mbar_expect_tx(in_full + 8u * st, Cfg::CHUNK_BYTES);
               tma_load_4d(sIn + st * Cfg::CHUNK_PITCH, &tmap_in, in_full + 8u * st, cc[g], cx[g], cy[g] + k * RC, ci[g]);
+              if (k == 0) rb_stamp(p.trace, 0, u0 + g, 0); else if (k == NCHK - 1) rb_stamp(p.trace, 0, u0 + g, 1);
               if (++stage[g] == NIG) { stage[g] = 0; phase[g] ^= 1u; }
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16_m128(COUT);
@@ -185,81 +194,102 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       tc_fence_after();
       int ul = 0;
       for (int lt = 0; lt < nt; ++lt) {
-        const uint32_t acc = (uint32_t)(lt & 1);
-        mbar_wait(tm_empty + 8u * acc, (((uint32_t)lt >> 1) & 1u) ^ 1u);   // epilogue drained this accumulator
+        const uint32_t acc = (uint32_t)lt % NACC;
+        mbar_wait(tm_empty + 8u * acc, (((uint32_t)lt / NACC) & 1u) ^ 1u);   // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * 256u;
+        const uint32_t tmem_d = tmem_base + acc * (uint32_t)COUT;
 #pragma unroll 1
         for (int kb = 0; kb < NKB; ++kb, ++ul) {
           const uint32_t st = (uint32_t)ul % NA, ph = ((uint32_t)ul / NA) & 1u;
+          rb_stamp(p.trace, 1, ul, 0);
           mbar_wait(a_full + 8u * st, ph);
           tc_fence_after();
+          rb_stamp(p.trace, 1, ul, 1);
           const uint64_t da = umma_desc_sw128(sA + st * RB_A_BYTES);
           const uint64_t db = umma_desc_sw128(sB + kb * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < CK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
           umma_commit(a_empty + 8u * st);
+          rb_stamp(p.trace, 1, ul, 2);
         }
         umma_commit(tm_full + 8u * acc);
       }
     }
-  } else if (warp < 2 + RB_EPI_WARPS) {
+  } else if (warp >= W_EPI) {
     // ======================= epilogue warps =======================
+    // A warp owns TMEM lanes 32*quarter .. +31 = tile rows 2*quarter, 2*quarter+1 and works on its own:
+    // private staging (NSTG x 4 KB) and its own TMA stores, so the four warps never meet.
     const int quarter = warp & 3;                          // TMEM lane quarter = warp % 4
-    const int m = quarter * 32 + lane;                     // TMEM lane = tile pixel r*TP + x
-    const int mr = m / RB_TP, mx = m % RB_TP;
-    const bool valid = mr < R && mx < TWO;
-    const int line = valid ? mr * TWO + mx : 0;            // row of the dense [R*TWO][64] staging block
-    const uint32_t line_off = (uint32_t)line * 128u, line_x = (uint32_t)(line & 7);
-    const bool leader = warp == 2 && lane == 0;
+    const int rsel = lane >> 4, mx = lane & 15;            // lane = rsel*TP + x
+    const bool valid = mx < TWO && 2 * quarter + rsel < R;
+    const int eset = (warp - W_EPI) >> 2;                   // epilogue set: tiles eset, eset + NE, ...
+    const uint32_t wbuf = sO + (uint32_t)(warp - W_EPI) * (NSTG * 4096u);
+    const uint32_t line = (uint32_t)(rsel * TWO + mx);      // dense [2][TWO] lines of 128 B, as the 2-row TMA box reads them
+    const uint32_t line_off = line * 128u, line_x = line & 7u;
+    const bool tracer = warp == W_EPI && lane == 0;
+    const int row0 = 2 * quarter;                          // first tile row of this warp
     uint32_t blk = 0;
-    for (int lt = 0; lt < nt; ++lt) {
-      const long tile = blockIdx.x + (long)lt * G;
-      const int img = (int)(tile / per_img), rem = (int)(tile - (long)img * per_img);
-      const int band = rem / p.strips, strip = rem - band * p.strips;
-      const uint32_t acc = (uint32_t)(lt & 1);
-      mbar_wait(tm_full + 8u * acc, ((uint32_t)lt >> 1) & 1u);
+    for (int lt = eset; lt < nt; lt += NE) {
+      const uint32_t tile = blockIdx.x + (uint32_t)lt * (uint32_t)G;
+      const uint32_t img = tile / (uint32_t)per_img, rem = tile - img * (uint32_t)per_img;
+      const uint32_t band = rem / (uint32_t)p.strips, strip = rem - band * (uint32_t)p.strips;
+      const uint32_t acc = (uint32_t)lt % NACC;
+      if (tracer) rb_stamp(p.trace, 2, lt, 0);
+      mbar_wait(tm_full + 8u * acc, ((uint32_t)lt / NACC) & 1u);
       tc_fence_after();
-#pragma unroll 1
+      if (tracer) rb_stamp(p.trace, 2, lt, 1);
+#pragma unroll
       for (int b = 0; b < COUT / 64; ++b, ++blk) {
-        const uint32_t sbuf = sO + (NSTG == 1 ? 0u : (blk % NSTG) * RB_O_BYTES);
-        if (leader) tma_store_wait_read<NSTG - 1>();         // the store that last read this buffer is done with it
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * RB_EPI_WARPS) : "memory");
+        const uint32_t sbuf = wbuf + (NSTG == 1 ? 0u : (blk % NSTG) * 4096u);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)COUT + (uint32_t)(b * 64);
+        uint32_t v[32];
+        if (!(p.dbg & 4)) tmem_ld32_nowait(taddr, v);
+        if (lane == 0) tma_store_wait_read<NSTG - 1>();      // the store that last read this buffer is done with it
+        __syncwarp();
+        if (!(p.dbg & 4)) {
+          // two 32-column halves through one set of 32 registers (the kernel is capped at 96 registers:
+          // 18 warps are allocated as 20); scale / shift are compile-time offsets into the constant bank
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t v[32];
-          tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256u + (uint32_t)(b * 64 + 32 * half), v);
-          tmem_ld_wait();
-          const uint32_t colb = (uint32_t)(b * 64 + 32 * half);
+          for (int half = 0; half < 2; ++half) {
+            if (tracer && b == 0 && half == 0) rb_stamp(p.trace, 6, lt, 0);
+            tmem_ld_wait();
+            if (tracer && b == 0 && half == 0) rb_stamp(p.trace, 6, lt, 1);
+            uint32_t q[16];
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const float4 s0 = lds128f(sPsc + (colb + j) * 4u), s1 = lds128f(sPsc + (colb + j + 4) * 4u);
-            const float4 t0 = lds128f(sPsh + (colb + j) * 4u), t1 = lds128f(sPsh + (colb + j + 4) * 4u);
-            const uint32_t q0 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 0]), s0.x, t0.x), fmaf(__uint_as_float(v[j + 1]), s0.y, t0.y), p.pw_cap2);
-            const uint32_t q1 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 2]), s0.z, t0.z), fmaf(__uint_as_float(v[j + 3]), s0.w, t0.w), p.pw_cap2);
-            const uint32_t q2 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 4]), s1.x, t1.x), fmaf(__uint_as_float(v[j + 5]), s1.y, t1.y), p.pw_cap2);
-            const uint32_t q3 = pack2<PW_RELU>(fmaf(__uint_as_float(v[j + 6]), s1.z, t1.z), fmaf(__uint_as_float(v[j + 7]), s1.w, t1.w), p.pw_cap2);
-            const uint32_t chunk = (uint32_t)(4 * half + j / 8);
-            if (valid) sts128(sbuf + line_off + ((chunk ^ line_x) << 4), q0, q1, q2, q3);
+            for (int j = 0; j < 32; j += 2) {
+              const int col = b * 64 + half * 32 + j;
+              q[j / 2] = pack2<PW_RELU>(fmaf(__uint_as_float(v[j]), p.pw_scale[col], p.pw_shift[col]),
+                                        fmaf(__uint_as_float(v[j + 1]), p.pw_scale[col + 1], p.pw_shift[col + 1]), p.pw_cap2);
+            }
+            if (half == 0) tmem_ld32_nowait(taddr + 32u, v);   // v is free again: fetch the second half under the stores
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4)
+              if (valid) sts128(sbuf + line_off + (((uint32_t)(half * 4 + c4) ^ line_x) << 4), q[4 * c4], q[4 * c4 + 1], q[4 * c4 + 2], q[4 * c4 + 3]);
           }
         }
+        if (tracer && b == 0) rb_stamp(p.trace, 6, lt, 2);
         fence_proxy_async();
-        asm volatile("bar.sync 1, %0;" ::"n"(32 * RB_EPI_WARPS) : "memory");
-        if (leader) {
-          // box = 64 channels x TWO columns x R rows of one image; smem = dense [R*TWO][64], 128B swizzle
-          tma_store_4d(&tmap_out, sbuf, b * 64, strip * TWO, band * R, img);
+        __syncwarp();
+        if (tracer && b == 0) rb_stamp(p.trace, 6, lt, 3);
+        if (lane == 0 && !(p.dbg & 2)) {
+          // the warp's two tile rows as one box (64 channels x TWO columns x 2 rows; smem = 2 x [16][64]
+          // bf16, 128B swizzle), or the single-row box when the tile has an odd number of rows
+          const int y = (int)band * R + row0;
+          if (row0 + 1 < R) tma_store_4d(&tmap_out2, sbuf, b * 64, (int)strip * TWO, y, (int)img);
+          else if (row0 < R) tma_store_4d(&tmap_out, sbuf, b * 64, (int)strip * TWO, y, (int)img);
           tma_store_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tm_empty + 8u * acc);
+      if (tracer) rb_stamp(p.trace, 2, lt, 2);
     }
-    if (leader) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   } else {
     // ======================= stencil groups =======================
-    const int g = (warp - (2 + RB_EPI_WARPS)) / RB_GW;
-    const int t = tid - (2 + RB_EPI_WARPS + g * RB_GW) * 32;    // 0..127 inside the group
+    const int g = warp / GW;
+    const int t = tid - g * GW * 32;                      // thread index inside the group
     const bool active = t < PG * CQ;
     const int quad = t % CQ;
     const int pg = active ? t / CQ : PG - 1;
@@ -295,32 +325,44 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       const uint32_t ast = (uint32_t)ul % NA, aph = ((uint32_t)ul / NA) & 1u;
       const uint32_t dstA = sA + ast * RB_A_BYTES;
 
+      const bool tracer = t == 0;
+      if (tracer) rb_stamp(p.trace, 3 + g, ul / NG, 0);
       float acc[RING][TW][4];
-      uint32_t rowbase = 0, cur_stage = 0;
-#pragma unroll
-      for (int q = 0; q < HR; ++q) {
-        if (q % RC == 0) {                                  // next chunk of the unit
+      // The raw bf16 quads of input row q+1 are fetched while row q is being computed (one row of
+      // software pipelining: without it every row exposes the ld.shared latency to its FFMAs).
+      uint32_t rowbase = 0, cur_stage = 0, prev_stage = 0;
+      uint2 nraw[NCOL];
+      auto fetch_row = [&](int q) {                          // q is a compile-time constant at every call site
+        if (q % RC == 0) {                                   // first row of the next chunk of the unit
+          prev_stage = cur_stage;
           cur_stage = (uint32_t)(g * NIG) + rstage;
           mbar_wait(in_full + 8u * cur_stage, rphase);
+          if (q == 0 && tracer) rb_stamp(p.trace, 3 + g, ul / NG, 1);
           rowbase = sIn + cur_stage * Cfg::CHUNK_PITCH + in_off;
           if (++rstage == NIG) { rstage = 0; rphase ^= 1u; }
         }
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) nraw[j] = lds64(rowbase + (uint32_t)(((q % RC) * BW + j) * LINE));
+      };
+      fetch_row(0);
+#pragma unroll
+      for (int q = 0; q < HR; ++q) {
         float x[NCOL][4];
 #pragma unroll
         for (int j = 0; j < NCOL; ++j) {
-          const uint2 raw = lds64(rowbase + (uint32_t)(((q % RC) * BW + j) * LINE));
-          x[j][0] = bf16lo_to_f32(raw.x); x[j][1] = bf16hi_to_f32(raw.x);
-          x[j][2] = bf16lo_to_f32(raw.y); x[j][3] = bf16hi_to_f32(raw.y);
+          x[j][0] = bf16lo_to_f32(nraw[j].x); x[j][1] = bf16hi_to_f32(nraw[j].x);
+          x[j][2] = bf16lo_to_f32(nraw[j].y); x[j][3] = bf16hi_to_f32(nraw[j].y);
         }
-        if (q % RC == RC - 1 || q == HR - 1) {              // chunk consumed: hand the stage back
+        if (q + 1 < HR) fetch_row(q + 1);
+        if (q % RC == RC - 1 || q == HR - 1) {              // row q was the last of its chunk: hand the stage back
           __syncwarp();
-          if (lane == 0) mbar_arrive(in_empty + 8u * cur_stage);
+          if (lane == 0) mbar_arrive(in_empty + 8u * (((q + 1) % RC == 0 && q + 1 < HR) ? prev_stage : cur_stage));
         }
         // input row q feeds tap row tr of output row o = (q - tr) / S; tap rows accumulate in order
         // 0, 1, 2 (the order of depthwise_tma.cu), the shift seeds the accumulator
 #pragma unroll
         for (int tr = 2; tr >= 0; --tr) {
-          if ((q - tr) >= 0 && (q - tr) % S == 0 && (q - tr) / S < R) {
+          if ((q - tr) >= 0 && (q - tr) % S == 0 && (q - tr) / S < R ) {
             const int o = (q - tr) / S, slot = o % RING;
 #pragma unroll
             for (int c = 0; c < TW; ++c)
@@ -331,7 +373,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                                        fmaf(x[c * S + 1][v], w[3 * tr + 1][v], fmaf(x[c * S][v], w[3 * tr][v], init)));
               }
             if (tr == 2) {                                  // output row o is complete
-              if (o == 0) mbar_wait(a_empty + 8u * ast, aph ^ 1u);   // the MMAs that last read this A stage retired
+              if (o == 0) { mbar_wait(a_empty + 8u * ast, aph ^ 1u); if (tracer) rb_stamp(p.trace, 3 + g, ul / NG, 2); }   // the MMAs that last read this A stage retired
               if (active) {
 #pragma unroll
                 for (int c = 0; c < TW; ++c)
@@ -345,12 +387,13 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + 8u * ast);
+      if (tracer) rb_stamp(p.trace, 3 + g, ul / NG, 3);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
   }
@@ -364,7 +407,7 @@ cudaError_t launch_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
   constexpr int S = Cfg::S, C = Cfg::C, COUT = Cfg::COUT;
   const int Ho = H / S, Wo = W / S;
   if (Ho % Cfg::R || Wo % Cfg::TWO) return cudaErrorNotSupported;
-  CUtensorMap tin, tout;
+  CUtensorMap tin, tout, tout2;
   {
     cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
     cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
@@ -375,21 +418,34 @@ cudaError_t launch_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { if (err) *err = "fused block: input tensor map encode failed"; return cudaErrorInvalidValue; }
   }
-  {
+  for (int rows2 = 1; rows2 <= 2; ++rows2) {   // output boxes of one and of two tile rows
     cuuint64_t gdim[4] = {(cuuint64_t)COUT, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)n};
     cuuint64_t gstr[3] = {(cuuint64_t)COUT * 2, (cuuint64_t)Wo * COUT * 2, (cuuint64_t)Ho * Wo * COUT * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)Cfg::TWO, (cuuint32_t)Cfg::R, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)Cfg::TWO, (cuuint32_t)rows2, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(&tout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(rows2 == 1 ? &tout : &tout2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { if (err) *err = "fused block: output tensor map encode failed"; return cudaErrorInvalidValue; }
   }
   RbParams p{};
-  p.dw_taps = dw->w_scaled; p.dw_shift = dw->shift; p.pw_scale = pw->scale; p.pw_shift = pw->shift;
+  p.dw_taps = dw->w_scaled; p.dw_shift = dw->shift;
+  for (int i = 0; i < 256; ++i) {
+    p.pw_scale[i] = i < (int)pw->h_scale.size() ? pw->h_scale[i] : 1.f;
+    p.pw_shift[i] = i < (int)pw->h_shift.size() ? pw->h_shift[i] : 0.f;
+  }
   p.dw_cap2 = dw->act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
   p.pw_cap2 = pw->act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
   p.bands = Ho / Cfg::R; p.strips = Wo / Cfg::TWO; p.pad_lo = pad_lo;
   p.tiles = (long)n * p.bands * p.strips;
+  p.dbg = getenv("MNV1_RB_DBG") ? atoi(getenv("MNV1_RB_DBG")) : 0;
+  static unsigned long long* d_trace = nullptr;
+  const bool tracing = getenv("MNV1_RB_TRACE") != nullptr;
+  if (tracing) {
+    if (!d_trace) cudaMalloc(&d_trace, 8 * 128 * 4 * 8);
+    cudaMemsetAsync(d_trace, 0, 8 * 128 * 4 * 8, st);
+    p.trace = d_trace;
+  }
   const bool dr = dw->act != MNV1_ACT_NONE, pr = pw->act != MNV1_ACT_NONE;
   long grid = num_sms;
   if (grid > p.tiles) grid = p.tiles;
@@ -402,19 +458,25 @@ cudaError_t launch_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-#define RB_LAUNCH(A, B) fused_rb_kernel<Cfg, A, B><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(tin, pw->tmap_b, tout, p)
+#define RB_LAUNCH(A, B) fused_rb_kernel<Cfg, A, B><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(tin, pw->tmap_b, tout, tout2, p)
   if (dr) { if (pr) RB_LAUNCH(true, true); else RB_LAUNCH(true, false); }
   else    { if (pr) RB_LAUNCH(false, true); else RB_LAUNCH(false, false); }
 #undef RB_LAUNCH
+  if (tracing) {   // debug only: dump the stamps of the last launch
+    std::vector<unsigned long long> h(8 * 128 * 4);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(getenv("MNV1_RB_TRACE"), "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+  }
   return cudaGetLastError();
 }
 
-//                   S  CK NKB COUT TWO R TW RC NG NIG NA NSTG
-using CfgL02 = RbCfg<1, 32, 1,  64, 16, 8, 1, 5, 3, 6, 3, 2>;   // 112x112x32  -> 112x112x64
-using CfgL04 = RbCfg<2, 64, 1, 128, 14, 8, 2, 2, 3, 5, 3, 2>;   // 112x112x64  -> 56x56x128
-using CfgL06 = RbCfg<1, 64, 2, 128, 14, 8, 2, 5, 3, 3, 3, 2>;   // 56x56x128   -> 56x56x128
-using CfgL08 = RbCfg<2, 64, 2, 256, 14, 7, 2, 2, 3, 4, 3, 1>;   // 56x56x128   -> 28x28x256
-using CfgL10 = RbCfg<1, 64, 4, 256, 14, 7, 2, 3, 2, 3, 2, 1>;   // 28x28x256   -> 28x28x256
+//                   S  CK NKB COUT TWO R TW  RC NG GW NIG NA NE NSTG
+using CfgL02 = RbCfg<1, 32, 1,  64, 16, 8, 1, 10, 2, 4, 3, 4, 2, 2>;   // 112x112x32  -> 112x112x64
+using CfgL04 = RbCfg<2, 64, 1, 128, 14, 8, 2,  2, 3, 4, 5, 3, 1, 2>;   // 112x112x64  -> 56x56x128
+using CfgL06 = RbCfg<1, 64, 2, 128, 14, 8, 2,  5, 3, 4, 3, 3, 1, 2>;   // 56x56x128   -> 56x56x128
+using CfgL08 = RbCfg<2, 64, 2, 256, 14, 7, 2,  2, 3, 4, 4, 3, 1, 1>;   // 56x56x128   -> 28x28x256
+using CfgL10 = RbCfg<1, 64, 4, 256, 14, 7, 2,  3, 2, 4, 3, 2, 1, 1>;   // 28x28x256   -> 28x28x256
 
 }  // namespace
 

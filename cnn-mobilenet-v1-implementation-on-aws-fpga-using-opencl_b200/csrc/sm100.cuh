@@ -24,18 +24,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// try_wait with a suspend-time hint: the warp sleeps in hardware instead of burning issue slots
+// try_wait without a suspend-time hint: the warp sleeps inside TRYWAIT for the hardware's own
+// window and is woken by the arrive.  (With an explicit hint ptxas emits TRYWAIT + NANOSLEEP.SYNCS,
+// whose wake-up is far slower: a hand-shake per 128-pixel tile then costs microseconds.)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "MBAR_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra MBAR_DONE;\n"
       "bra MBAR_WAIT;\n"
       "MBAR_DONE:\n"
       "}\n" ::"r"(bar),
-      "r"(parity), "r"(20000u)
+      "r"(parity)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
@@ -134,6 +136,13 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+// read-only shared data (constants staged once per CTA): not volatile, so the compiler may hoist,
+// batch and reorder these loads freely
+__device__ __forceinline__ float4 lds128f_ro(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
