@@ -87,27 +87,45 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def layer_roofline(layers, times_ms, n, peaks):
-    """Per-layer achieved GB/s / TFLOP/s against min(HBM, tensor) (SURVEY App. B definitions:
-    bytes = (in+out)*2 per image + weights*2 once; the stem's input counted as raw u8)."""
+def layer_roofline(layers, times_ms, n, peaks, fused=None):
+    """Per-launch achieved GB/s / TFLOP/s against min(HBM, tensor) (SURVEY 8d / App. B definitions:
+    bytes = (in+out)*2 per image + weights*2 once; the stem's input counted as raw u8).  A depthwise
+    layer that runs fused with the pointwise after it is ONE row ("dw+pw"): its algorithmic bytes
+    are the depthwise input + the pointwise output + both filters (the depthwise map never leaves
+    the SM), its FLOPs the sum."""
     from mnv1_b200.layers import STEM, DEPTHWISE, POINTWISE, POOL, FC
     rows = []
-    for L, t in zip(layers, times_ms):
+    i = 0
+    while i < len(layers):
+        L, t = layers[i], float(times_ms[i])
         in_b = L.in_elems * (1 if L.kind == STEM else 2)
         out_b = L.out_elems * (4 if L.kind in (POOL, FC) else 2)
         wbytes = L.w_cnt * (4 if L.kind in (STEM, DEPTHWISE) else 2)
-        nbytes = (in_b + out_b) * n + wbytes
         flops = 2.0 * L.macs * n
+        tc_flops = flops if L.kind == POINTWISE else 0.0
+        kind = ["stem", "dw", "pw", "pool", "fc"][L.kind]
+        cout, hout, label = L.cout, L.hout, str(L.index)
+        if fused is not None and fused[i] and i + 1 < len(layers):
+            P = layers[i + 1]
+            t += float(times_ms[i + 1])
+            out_b = P.out_elems * 2
+            wbytes += P.w_cnt * 2
+            flops += 2.0 * P.macs * n
+            tc_flops = 2.0 * P.macs * n
+            kind, cout, hout, label = "dw+pw", P.cout, P.hout, f"{L.index}+{P.index}"
+            i += 1
+        nbytes = (in_b + out_b) * n + wbytes
         t_hbm = nbytes / (peaks["hbm_gbs"] * 1e9)
-        t_tc = flops / (peaks["bf16_tflops"] * 1e12) if L.kind == POINTWISE else 0.0
+        t_tc = tc_flops / (peaks["bf16_tflops"] * 1e12)
         t_roof = max(t_hbm, t_tc)
         sec = t * 1e-3
-        rows.append({"layer": L.index, "kind": ["stem", "dw", "pw", "pool", "fc"][L.kind], "cin": L.cin,
-                     "cout": L.cout, "hout": L.hout, "stride": L.stride, "us": round(t * 1e3, 2),
+        rows.append({"layer": label, "kind": kind, "cin": L.cin, "cout": cout, "hout": hout, "stride": L.stride,
+                     "us": round(t * 1e3, 2),
                      "gbs": round(nbytes / sec / 1e9, 1) if sec > 0 else None,
                      "tflops": round(flops / sec / 1e12, 2) if sec > 0 else None,
                      "bound": "tensor" if t_tc > t_hbm else "hbm", "roof_us": round(t_roof * 1e6, 2),
                      "frac": round(t_roof / sec, 3) if sec > 0 else None, "bytes": nbytes, "flops": flops})
+        i += 1
     return rows
 
 
@@ -234,7 +252,7 @@ def run_ours(args):
         rows, roof = None, None
         if rank == 0:
             lt = ctx.profile_layers(imgs[1].data_ptr(), batch, iters=10)
-            rows = layer_roofline(LAYERS, lt, batch, peaks)
+            rows = layer_roofline(LAYERS, lt, batch, peaks, ctx.fused_layers())
             fam = {}
             for r in rows:
                 f = fam.setdefault(r["kind"], {"us": 0.0, "bytes": 0.0, "flops": 0.0, "roof_us": 0.0, "n": 0})
@@ -248,11 +266,12 @@ def run_ours(args):
             if os.path.exists(tpath):
                 traffic = json.load(open(tpath)).get(dom)
             ach = d["bytes"] / (d["us"] * 1e-6) / 1e9
-            roof = {"kernel": {"dw": "depthwise_kernel", "pw": "pointwise_tc_kernel", "stem": "stem_kernel",
-                               "pool": "pool_kernel", "fc": "head"}[dom],
+            roof = {"kernel": {"dw": "depthwise_tma_kernel", "pw": "pointwise_tc_kernel", "stem": "stem_tc_kernel",
+                               "dw+pw": "fused_rb_kernel", "pool": "pool_kernel", "fc": "head"}[dom],
                     "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": round(ach / peaks["hbm_gbs"], 3), "traffic": traffic,
                     "launches_per_step": d["n"], "bytes_per_step": d["bytes"], "us_per_step": round(d["us"], 1),
+                    "bytes_per_launch": round(d["bytes"] / d["n"]), "us_per_launch": round(d["us"] / d["n"], 1),
                     "share_of_step": round(d["us"] / total_us, 3), "peak_source": peaks["source"],
                     "families": {k: {"us": round(v["us"], 1), "share": round(v["us"] / total_us, 3),
                                      "frac_of_roofline": round(v["roof_us"] / v["us"], 3)} for k, v in fam.items()},

@@ -220,6 +220,12 @@ class Context:
     def use_fused_blocks(self, on: bool):
         self._ck(lib().mnv1_ctx_use_fused_blocks(self.h, int(on)))
 
+    def fused_layers(self) -> np.ndarray:
+        """fused[i] = 1: mnv1_forward runs depthwise layer i+1 and the pointwise after it as one kernel."""
+        f = np.zeros(29, dtype=np.int32)
+        self._ck(lib().mnv1_fused_layers(self.h, _vp(f)))
+        return f
+
     def pool(self, out: Buffer, inp: Buffer, rows, cols, filtersize, op_size):
         self._ck(lib().mnv1_pool(self.h, out.h, inp.h, rows, cols, filtersize, op_size))
 

@@ -840,6 +840,20 @@ int mnv1_dw_pw_block(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv
   return MNV1_OK;
 }
 
+// fused[i] = 1 when mnv1_forward* runs layer i+1 (a depthwise) and the pointwise after it as one kernel
+int mnv1_fused_layers(mnv1_ctx* ctx, int* fused) {
+  if (!ctx || !fused) return fail(ctx, MNV1_EINVAL, "fused_layers: null argument");
+  if (!ctx->have_weights) return fail(ctx, MNV1_ESTATE, "weights not loaded (mnv1_set_weights / mnv1_load_weights)");
+  const LayerDef* L = layer_defs();
+  for (int i = 0; i < MNV1_NUM_LAYERS; ++i) {
+    fused[i] = 0;
+    if (ctx->use_fused && ctx->dtype == MNV1_BF16 && L[i].kind == MNV1_DEPTHWISE && i + 1 < MNV1_NUM_LAYERS &&
+        L[i + 1].kind == MNV1_POINTWISE)
+      fused[i] = mnv1::fused_dw_pw_supported(ctx->net[i], ctx->net[i + 1], L[i].hin, L[i].hin, L[i].stride) ? 1 : 0;
+  }
+  return MNV1_OK;
+}
+
 int mnv1_ctx_use_graph(mnv1_ctx* ctx, int on) {
   if (!ctx) return MNV1_EINVAL;
   ctx->use_graph = on != 0;

@@ -105,6 +105,8 @@ cudaError_t make_weight_tmap(mnv1_filter* f, std::string* err);
 cudaError_t launch_fused_dw_pw(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n,
                                int rows, int cols, int stride, int pad_lo, int num_sms, cudaStream_t st,
                                std::string* err);
+bool fused_dw_pw_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride);
+bool fused_rb_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride);
 // resident-filter variant (fused_rb.cu): blocks whose pointwise filter fits in shared memory
 cudaError_t launch_fused_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n, int rows,
                             int cols, int stride, int pad_lo, int num_sms, cudaStream_t st, std::string* err);

@@ -433,6 +433,22 @@ cudaError_t launch_fb(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
 
 }  // namespace
 
+namespace {
+// The 14x14 streaming-filter variant is kept for experiments (MNV1_FB=1): it re-reads the whole
+// pointwise filter from L2 for every 98-pixel item and is slower than the two separate kernels.
+bool fb_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride) {
+  static const bool fb_on = getenv("MNV1_FB") != nullptr;
+  if (!fb_on) return false;
+  if (stride != 1 || !dw->w_scaled || !pw->has_tmap || pw->tmap_bn != 256 || pw->cin != dw->cout) return false;
+  if (dw->cout % 64 || pw->cout % 256 || pw->cout > 512 || dw->cout > 1024) return false;
+  return rows == 14 && cols == 14;
+}
+}  // namespace
+
+bool fused_dw_pw_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride) {
+  return fused_rb_supported(dw, pw, rows, cols, stride) || fb_supported(dw, pw, rows, cols, stride);
+}
+
 // cudaErrorNotSupported (nothing launched) when the block shape has no fused variant.
 cudaError_t launch_fused_dw_pw(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n,
                                int rows, int cols, int stride, int pad_lo, int num_sms, cudaStream_t st,
@@ -441,13 +457,9 @@ cudaError_t launch_fused_dw_pw(bf16* out, const bf16* in, const mnv1_filter* dw,
     cudaError_t e = launch_fused_rb(out, in, dw, pw, n, rows, cols, stride, pad_lo, num_sms, st, err);
     if (e != cudaErrorNotSupported) return e;
   }
-  static const bool fb_on = !getenv("MNV1_NO_FB");   // debug switch for the 14x14 variant
-  if (!fb_on) return cudaErrorNotSupported;
-  if (stride != 1 || !dw->w_scaled || !pw->has_tmap || pw->tmap_bn != 256 || pw->cin != dw->cout) return cudaErrorNotSupported;
-  if (dw->cout % 64 || pw->cout % 256 || pw->cout > 512 || dw->cout > 1024) return cudaErrorNotSupported;
+  if (!fb_supported(dw, pw, rows, cols, stride)) return cudaErrorNotSupported;
   if (n <= 0) return cudaSuccess;
-  if (rows == 14 && cols == 14) return launch_fb<14, 7>(out, in, dw, pw, n, rows, num_sms, st, err);
-  return cudaErrorNotSupported;
+  return launch_fb<14, 7>(out, in, dw, pw, n, rows, num_sms, st, err);
 }
 
 }  // namespace mnv1

@@ -480,23 +480,43 @@ using CfgL10 = RbCfg<1, 64, 4, 256, 14, 7, 2,  3, 2, 4, 3, 2, 1, 1>;   // 28x28x
 
 }  // namespace
 
+namespace {
+// index of the variant that handles this block, or -1
+int rb_variant(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride) {
+  if (!dw->w_scaled || !pw->has_tmap || pw->cin != dw->cout || pw->tmap_bn != pw->cout) return -1;
+  // MNV1_RB_MASK (debug): bit i enables the i-th variant below; default all
+  static const long mask = getenv("MNV1_RB_MASK") ? strtol(getenv("MNV1_RB_MASK"), nullptr, 0) : ~0L;
+  const int c = dw->cout, co = pw->cout;
+#define RB_IS(CFG, HW, BIT) \
+  if ((mask >> BIT & 1) && stride == CFG::S && c == CFG::C && co == CFG::COUT && rows == HW && cols == HW && \
+      (HW / CFG::S) % CFG::R == 0 && (HW / CFG::S) % CFG::TWO == 0) return BIT
+  RB_IS(CfgL02, 112, 0);
+  RB_IS(CfgL04, 112, 1);
+  RB_IS(CfgL06, 56, 2);
+  RB_IS(CfgL08, 56, 3);
+  RB_IS(CfgL10, 28, 4);
+#undef RB_IS
+  return -1;
+}
+}  // namespace
+
+bool fused_rb_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride) {
+  return rb_variant(dw, pw, rows, cols, stride) >= 0;
+}
+
 // cudaErrorNotSupported (nothing launched) when the block has no resident-filter variant.
 cudaError_t launch_fused_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n, int rows,
                             int cols, int stride, int pad_lo, int num_sms, cudaStream_t st, std::string* err) {
-  if (!dw->w_scaled || !pw->has_tmap || pw->cin != dw->cout || pw->tmap_bn != pw->cout) return cudaErrorNotSupported;
+  const int v = rb_variant(dw, pw, rows, cols, stride);
+  if (v < 0) return cudaErrorNotSupported;
   if (n <= 0) return cudaSuccess;
-  const int c = dw->cout, co = pw->cout;
-  // MNV1_RB_MASK (debug): bit i enables the i-th variant below; default all
-  static const long mask = getenv("MNV1_RB_MASK") ? strtol(getenv("MNV1_RB_MASK"), nullptr, 0) : ~0L;
-#define RB_TRY(CFG, HW, BIT) \
-  if ((mask >> BIT & 1) && stride == CFG::S && c == CFG::C && co == CFG::COUT && rows == HW && cols == HW) \
-    return launch_rb<CFG>(out, in, dw, pw, n, rows, cols, pad_lo, num_sms, st, err)
-  RB_TRY(CfgL02, 112, 0);
-  RB_TRY(CfgL04, 112, 1);
-  RB_TRY(CfgL06, 56, 2);
-  RB_TRY(CfgL08, 56, 3);
-  RB_TRY(CfgL10, 28, 4);
-#undef RB_TRY
+  switch (v) {
+    case 0: return launch_rb<CfgL02>(out, in, dw, pw, n, rows, cols, pad_lo, num_sms, st, err);
+    case 1: return launch_rb<CfgL04>(out, in, dw, pw, n, rows, cols, pad_lo, num_sms, st, err);
+    case 2: return launch_rb<CfgL06>(out, in, dw, pw, n, rows, cols, pad_lo, num_sms, st, err);
+    case 3: return launch_rb<CfgL08>(out, in, dw, pw, n, rows, cols, pad_lo, num_sms, st, err);
+    case 4: return launch_rb<CfgL10>(out, in, dw, pw, n, rows, cols, pad_lo, num_sms, st, err);
+  }
   return cudaErrorNotSupported;
 }
 

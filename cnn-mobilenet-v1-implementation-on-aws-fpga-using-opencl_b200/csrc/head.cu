@@ -83,25 +83,41 @@ __global__ void __launch_bounds__(256, 1) fc_kernel(float* __restrict__ out, con
   for (int c = 0; c < FC_WCLS; ++c)
 #pragma unroll
     for (int im = 0; im < FC_IMGS; ++im) acc[c][im] = 0.f;
-  for (int k0 = 0; k0 < k; k0 += 256) {
-    // this lane's 8 contraction indices of the step: k0 + lane*4 + {0..3} and + 128
-    const int ka = k0 + lane * 4, kb = ka + 128;
-    float wv[FC_WCLS][8];
+  // The filter rows stream straight from L2; the 16 loads of step k0+256 are issued before the 512
+  // FFMAs of step k0 (register double buffer), so their latency hides under the arithmetic.
+  auto load_w = [&](int k0, uint2 (&r)[FC_WCLS][2], float4 (&f)[FC_WCLS][2]) {
+    const int ka = k0 + lane * 4, kb = ka + 128;   // this lane's 8 contraction indices of the step
 #pragma unroll
     for (int c = 0; c < FC_WCLS; ++c) {
       const int cls = min(clsw + c, classes - 1);  // clamp: rows past the end are computed but never stored
       if constexpr (sizeof(TW) == 2) {
-        const uint2 r0 = __ldg(reinterpret_cast<const uint2*>(w + (long)cls * k + ka));
-        const uint2 r1 = __ldg(reinterpret_cast<const uint2*>(w + (long)cls * k + kb));
+        r[c][0] = __ldg(reinterpret_cast<const uint2*>(w + (long)cls * k + ka));
+        r[c][1] = __ldg(reinterpret_cast<const uint2*>(w + (long)cls * k + kb));
+      } else {
+        f[c][0] = __ldg(reinterpret_cast<const float4*>(w + (long)cls * k + ka));
+        f[c][1] = __ldg(reinterpret_cast<const float4*>(w + (long)cls * k + kb));
+      }
+    }
+  };
+  uint2 rn[FC_WCLS][2];
+  float4 fn[FC_WCLS][2];
+  load_w(0, rn, fn);
+  for (int k0 = 0; k0 < k; k0 += 256) {
+    const int ka = k0 + lane * 4, kb = ka + 128;
+    float wv[FC_WCLS][8];
+#pragma unroll
+    for (int c = 0; c < FC_WCLS; ++c) {
+      if constexpr (sizeof(TW) == 2) {
+        const uint2 r0 = rn[c][0], r1 = rn[c][1];
         wv[c][0] = bf16lo_to_f32(r0.x); wv[c][1] = bf16hi_to_f32(r0.x); wv[c][2] = bf16lo_to_f32(r0.y); wv[c][3] = bf16hi_to_f32(r0.y);
         wv[c][4] = bf16lo_to_f32(r1.x); wv[c][5] = bf16hi_to_f32(r1.x); wv[c][6] = bf16lo_to_f32(r1.y); wv[c][7] = bf16hi_to_f32(r1.y);
       } else {
-        const float4 r0 = __ldg(reinterpret_cast<const float4*>(w + (long)cls * k + ka));
-        const float4 r1 = __ldg(reinterpret_cast<const float4*>(w + (long)cls * k + kb));
+        const float4 r0 = fn[c][0], r1 = fn[c][1];
         wv[c][0] = r0.x; wv[c][1] = r0.y; wv[c][2] = r0.z; wv[c][3] = r0.w;
         wv[c][4] = r1.x; wv[c][5] = r1.y; wv[c][6] = r1.z; wv[c][7] = r1.w;
       }
     }
+    if (k0 + 256 < k) load_w(k0 + 256, rn, fn);
 #pragma unroll
     for (int im = 0; im < FC_IMGS; ++im) {
       const float4 a0 = *reinterpret_cast<const float4*>(&s_a[im * k + ka]);
@@ -138,6 +154,90 @@ __global__ void __launch_bounds__(256, 1) fc_kernel(float* __restrict__ out, con
   }
 }
 
+// FC for bf16 contexts on the tensor cores without giving up the fp32 pooled means: every fp32 activation
+// is split exactly into three bf16 pieces (x = hi + mid + lo, 8 mantissa bits each, by truncation), the
+// bf16 filter is used as is, and three mma.sync.m16n8k16 per filter fragment accumulate the exact
+// bf16 x bf16 products in fp32.  A warp owns 16 images x 32 classes; fragments come straight from L2
+// with 128-bit loads (the contraction index is permuted the same way for both operands, so each lane
+// reads 8 consecutive k per 32-wide step) and the loads of step i+1 are issued before the MMAs of step i.
+// The four warps of a CTA split the contraction (k/4 each, summed in a fixed order through shared memory):
+// 512 CTAs of short dependent chains instead of 128 long ones — the kernel is latency-, not math-bound.
+// The legacy mma.sync path is deliberate: M = 256 is two tcgen05 tiles — not enough CTAs to matter.
+constexpr int FCM_NT = 4;        // 8-class fragments per warp (a CTA owns 16 images x 32 classes)
+constexpr int FCM_WARPS = 4;     // warps per CTA = k-splits
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// x0, x1 -> packed bf16 pairs of the three exact pieces
+__device__ __forceinline__ void split3(float x0, float x1, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+  const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
+  const uint32_t h0 = u0 & 0xffff0000u, h1 = u1 & 0xffff0000u;
+  const float r0 = x0 - __uint_as_float(h0), r1 = x1 - __uint_as_float(h1);          // exact
+  const uint32_t m0 = __float_as_uint(r0) & 0xffff0000u, m1 = __float_as_uint(r1) & 0xffff0000u;
+  const float s0 = r0 - __uint_as_float(m0), s1 = r1 - __uint_as_float(m1);          // exact, <= 8 significant bits
+  hi = (h0 >> 16) | h1;
+  mid = (m0 >> 16) | m1;
+  lo = (__float_as_uint(s0) >> 16) | (__float_as_uint(s1) & 0xffff0000u);
+}
+__global__ void __launch_bounds__(FCM_WARPS * 32) fc_mma_kernel(float* __restrict__ out, const float* __restrict__ pooled,
+                                                                const bf16* __restrict__ w, const float* __restrict__ bias,
+                                                                int n, int k, int classes) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  __shared__ float s_part[FCM_WARPS][16][FCM_NT * 8 + 1];
+  const int img0 = blockIdx.y * 16, cls0 = blockIdx.x * (FCM_NT * 8);
+  const int kw = k / FCM_WARPS, k_lo = warp * kw, k_hi = k_lo + kw;   // this warp's share of the contraction
+  const int r0 = min(img0 + g, n - 1), r1 = min(img0 + g + 8, n - 1);       // clamped rows are computed, never stored
+  const float* a0p = pooled + (long)r0 * k + 8 * t;
+  const float* a1p = pooled + (long)r1 * k + 8 * t;
+  const bf16* bp[FCM_NT];
+#pragma unroll
+  for (int j = 0; j < FCM_NT; ++j) bp[j] = w + (long)min(cls0 + 8 * j + g, classes - 1) * k + 8 * t;
+  float acc[FCM_NT][4];
+#pragma unroll
+  for (int j = 0; j < FCM_NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  float4 an[4];
+  uint4 bn[FCM_NT];
+  auto load = [&](int kb) {   // 32 contraction indices per step: this lane's are kb + 8t .. 8t+7
+    an[0] = __ldg(reinterpret_cast<const float4*>(a0p + kb)); an[1] = __ldg(reinterpret_cast<const float4*>(a0p + kb + 4));
+    an[2] = __ldg(reinterpret_cast<const float4*>(a1p + kb)); an[3] = __ldg(reinterpret_cast<const float4*>(a1p + kb + 4));
+#pragma unroll
+    for (int j = 0; j < FCM_NT; ++j) bn[j] = __ldg(reinterpret_cast<const uint4*>(bp[j] + kb));
+  };
+  load(k_lo);
+  for (int kb = k_lo; kb < k_hi; kb += 32) {
+    const float4 a00 = an[0], a01 = an[1], a10 = an[2], a11 = an[3];
+    uint4 b[FCM_NT];
+#pragma unroll
+    for (int j = 0; j < FCM_NT; ++j) b[j] = bn[j];
+    if (kb + 32 < k_hi) load(kb + 32);
+    // MMA slot k = (2t, 2t+1 | 2t+8, 2t+9) of step s <- this lane's elements (4s, 4s+1 | 4s+2, 4s+3)
+    uint32_t ah[2][4], am[2][4], al[2][4];
+    split3(a00.x, a00.y, ah[0][0], am[0][0], al[0][0]); split3(a10.x, a10.y, ah[0][1], am[0][1], al[0][1]);
+    split3(a00.z, a00.w, ah[0][2], am[0][2], al[0][2]); split3(a10.z, a10.w, ah[0][3], am[0][3], al[0][3]);
+    split3(a01.x, a01.y, ah[1][0], am[1][0], al[1][0]); split3(a11.x, a11.y, ah[1][1], am[1][1], al[1][1]);
+    split3(a01.z, a01.w, ah[1][2], am[1][2], al[1][2]); split3(a11.z, a11.w, ah[1][3], am[1][3], al[1][3]);
+#pragma unroll
+    for (int j = 0; j < FCM_NT; ++j) {
+      mma_bf16_16816(acc[j], al[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], al[1], b[j].z, b[j].w);   // small pieces first
+      mma_bf16_16816(acc[j], am[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], am[1], b[j].z, b[j].w);
+      mma_bf16_16816(acc[j], ah[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], ah[1], b[j].z, b[j].w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < FCM_NT; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s_part[warp][g + 8 * (e >> 1)][8 * j + 2 * t + (e & 1)] = acc[j][e];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * FCM_NT * 8; i += FCM_WARPS * 32) {
+    const int r = i / (FCM_NT * 8), c = i % (FCM_NT * 8);
+    const int img = img0 + r, cls = cls0 + c;
+    if (img < n && cls < classes)
+      out[(long)img * classes + cls] = ((s_part[0][r][c] + s_part[1][r][c]) + (s_part[2][r][c] + s_part[3][r][c])) + (bias ? __ldg(bias + cls) : 0.f);
+  }
+}
+
 cudaError_t launch_fc(float* out, const float* pooled, const float* w_f32, const bf16* w_bf16, const float* bias, int n,
                       int k, int classes, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
@@ -153,15 +253,76 @@ cudaError_t launch_fc(float* out, const float* pooled, const float* w_f32, const
     attr_set = true;
   }
   if (smem > 96 * 1024) return cudaErrorNotSupported;
+  if (w_bf16 && k % (32 * FCM_WARPS) == 0) {   // bf16 filter: tensor cores, exact fp32 activations (three bf16 pieces)
+    dim3 g2((classes + FCM_NT * 8 - 1) / (FCM_NT * 8), (n + 15) / 16);
+    fc_mma_kernel<<<g2, FCM_WARPS * 32, 0, st>>>(out, pooled, w_bf16, bias, n, k, classes);
+    return cudaGetLastError();
+  }
   if (w_bf16) fc_kernel<bf16><<<grid, 256, smem, st>>>(out, pooled, w_bf16, bias, n, k, classes);
   else fc_kernel<float><<<grid, 256, smem, st>>>(out, pooled, w_f32, bias, n, k, classes);
   return cudaGetLastError();
 }
 
-// one warp per image: max / argmax, sum of exp, optional probabilities — warp shuffles only.
-__global__ void __launch_bounds__(128) softmax_kernel(const float* __restrict__ logits, int n, int classes,
-                                                      float* __restrict__ prob, int* __restrict__ top1,
-                                                      float* __restrict__ top1_prob) {
+// one 128-thread CTA per image: every thread holds up to 8 logits in registers (all loads in flight
+// at once), warp shuffles + a 4-entry shared fold for max / argmax and the sum of exp.  First maximum
+// wins (strict `>` at MobileNet.c:2786).
+constexpr int SM_THREADS = 128, SM_PER = 8;
+__global__ void __launch_bounds__(SM_THREADS) softmax_kernel(const float* __restrict__ logits, int n, int classes,
+                                                             float* __restrict__ prob, int* __restrict__ top1,
+                                                             float* __restrict__ top1_prob) {
+  __shared__ float s_mx[4], s_sum[4];
+  __shared__ int s_arg[4];
+  const int img = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* z = logits + (long)img * classes;
+  float v[SM_PER];
+#pragma unroll
+  for (int i = 0; i < SM_PER; ++i) {
+    const int k = threadIdx.x + i * SM_THREADS;
+    v[i] = k < classes ? z[k] : -INFINITY;
+  }
+  float mx = -INFINITY;
+  int arg = 0x7fffffff;
+#pragma unroll
+  for (int i = 0; i < SM_PER; ++i)
+    if (v[i] > mx) { mx = v[i]; arg = threadIdx.x + i * SM_THREADS; }   // indices increase with i: strict '>' keeps the first
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, off);
+    const int oarg = __shfl_xor_sync(0xffffffffu, arg, off);
+    if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
+  }
+  if (lane == 0) { s_mx[warp] = mx; s_arg[warp] = arg; }
+  __syncthreads();
+  mx = s_mx[0]; arg = s_arg[0];
+#pragma unroll
+  for (int w = 1; w < 4; ++w)
+    if (s_mx[w] > mx || (s_mx[w] == mx && s_arg[w] < arg)) { mx = s_mx[w]; arg = s_arg[w]; }
+  float e[SM_PER], sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < SM_PER; ++i) { e[i] = __expf(v[i] - mx); sum += e[i]; }   // exp(-inf) = 0 for the padding
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  if (lane == 0) s_sum[warp] = sum;
+  __syncthreads();
+  sum = (s_sum[0] + s_sum[1]) + (s_sum[2] + s_sum[3]);
+  const float inv = 1.0f / sum;
+  if (prob) {
+#pragma unroll
+    for (int i = 0; i < SM_PER; ++i) {
+      const int k = threadIdx.x + i * SM_THREADS;
+      if (k < classes) prob[(long)img * classes + k] = e[i] * inv;
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (top1) top1[img] = arg;
+    if (top1_prob) top1_prob[img] = inv;
+  }
+}
+
+// generic fallback (more than SM_THREADS * SM_PER classes): one warp per image
+__global__ void __launch_bounds__(128) softmax_warp_kernel(const float* __restrict__ logits, int n, int classes,
+                                                           float* __restrict__ prob, int* __restrict__ top1,
+                                                           float* __restrict__ top1_prob) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n) return;
   const float* z = logits + (long)warp * classes;
@@ -169,7 +330,7 @@ __global__ void __launch_bounds__(128) softmax_kernel(const float* __restrict__ 
   int arg = 0x7fffffff;
   for (int k = lane; k < classes; k += 32) {
     const float v = z[k];
-    if (v > mx) { mx = v; arg = k; }  // per lane indices increase, so strict '>' keeps the first
+    if (v > mx) { mx = v; arg = k; }
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
@@ -193,8 +354,8 @@ __global__ void __launch_bounds__(128) softmax_kernel(const float* __restrict__ 
 cudaError_t launch_softmax(const float* logits, int n, int classes, float* prob, int* top1, float* top1_prob,
                            cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  const unsigned grid = (unsigned)((n + 3) / 4);
-  softmax_kernel<<<grid, 128, 0, st>>>(logits, n, classes, prob, top1, top1_prob);
+  if (classes <= SM_THREADS * SM_PER) softmax_kernel<<<(unsigned)n, SM_THREADS, 0, st>>>(logits, n, classes, prob, top1, top1_prob);
+  else softmax_warp_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(logits, n, classes, prob, top1, top1_prob);
   return cudaGetLastError();
 }
 

@@ -178,6 +178,9 @@ int mnv1_pointwise_simt(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const 
 int mnv1_dw_pw_block(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* dw_filter,
                      const mnv1_filter* pw_filter, int rows, int cols, int stride);
 int mnv1_ctx_use_fused_blocks(mnv1_ctx* ctx, int on);
+/* fused[i] (i = 0..MNV1_NUM_LAYERS-1) = 1 when mnv1_forward* runs depthwise layer i+1 and the pointwise
+ * layer after it as one kernel (weights must be loaded); per-layer reports then merge the two rows */
+int mnv1_fused_layers(mnv1_ctx* ctx, int* fused);
 /* 1 (default): mnv1_forward* replays a captured CUDA graph; 0: launches the kernels eagerly */
 int mnv1_ctx_use_graph(mnv1_ctx* ctx, int on);
 /* page-locked host memory (CL_MEM_ALLOC_HOST_PTR analogue): mnv1_forward copies straight
