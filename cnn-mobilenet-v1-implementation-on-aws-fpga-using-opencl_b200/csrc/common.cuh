@@ -101,15 +101,11 @@ cudaError_t launch_pointwise_simt(mnv1_dtype dt, void* out, const void* in, cons
 cudaError_t launch_pointwise_tc(bf16* out, const bf16* in, const mnv1_filter* f, long m, int k,
                                 int cout, int num_sms, cudaStream_t st, std::string* err);
 cudaError_t make_weight_tmap(mnv1_filter* f, std::string* err);
-// fused depthwise -> pointwise block (bf16); cudaErrorNotSupported = no variant, nothing launched
+// fused depthwise -> pointwise block (bf16, fused_rb.cu); cudaErrorNotSupported = no variant, nothing launched
 cudaError_t launch_fused_dw_pw(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n,
                                int rows, int cols, int stride, int pad_lo, int num_sms, cudaStream_t st,
                                std::string* err);
 bool fused_dw_pw_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride);
-bool fused_rb_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride);
-// resident-filter variant (fused_rb.cu): blocks whose pointwise filter fits in shared memory
-cudaError_t launch_fused_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n, int rows,
-                            int cols, int stride, int pad_lo, int num_sms, cudaStream_t st, std::string* err);
 cudaError_t launch_pool(mnv1_dtype dt, void* out, const void* in, int n, int hw, int c, bool out_f32,
                         cudaStream_t st);
 // fused head: global average pool -> FC (+bias) -> softmax -> argmax

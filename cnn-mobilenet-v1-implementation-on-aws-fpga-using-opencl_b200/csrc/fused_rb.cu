@@ -42,7 +42,8 @@ constexpr uint32_t RB_O_BYTES = 4 * 4096;    // output staging per buffer: 4 war
 
 // S stride; CK channels per k-block; NKB k-blocks (C = CK*NKB); COUT; tile = R x TWO outputs;
 // TW output columns per stencil thread; RC input rows per chunk; NG stencil groups of GW warps; NIG
-// chunk stages per group; NA A-tile stages (a multiple of NG: a stage always belongs to one group); NE
+// chunk stages per group; NA >= NG A-tile stages (unit u uses stage u % NA; the MMAs retire in order, so a
+// group can never be two uses of a stage ahead of its a_empty barrier); NE
 // epilogue sets of 4 warps (set e takes tiles e, e+NE, ...); NSTG output staging buffers per warp.
 template <int S_, int CK_, int NKB_, int COUT_, int TWO_, int R_, int TW_, int RC_, int NG_, int GW_, int NIG_, int NA_, int NE_, int NSTG_>
 struct RbCfg {
@@ -77,7 +78,7 @@ struct RbCfg {
   static_assert(TWO % TW == 0 && PG * CQ <= GW * 32, "tile does not fit a stencil group");
   static_assert(CK == 32 || CK == 64, "k-block is 32 or 64 channels");
   static_assert(COUT % 64 == 0 && COUT <= 256, "Cout: multiple of 64, at most 256 (two TMEM stages)");
-  static_assert(NA % NG == 0 && NIG >= 2, "A stages are owned by one group each; rings hold at least two chunks");
+  static_assert(NA >= NG && NIG >= 2, "an A stage per group at least; rings hold at least two chunks");
   static_assert(SMEM <= 227 * 1024, "shared memory budget exceeded");
 };
 
@@ -137,6 +138,10 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     for (int s = 0; s < NACC; ++s) { mbar_init(tm_full + 8u * s, 1); mbar_init(tm_empty + 8u * s, RB_EPI_WARPS); }
     mbar_init(b_full, 1);
     mbar_init_fence();
+  }
+  if (p.trace && blockIdx.x == 0 && tid == 0) {           // debug: SM clock vs wall clock over the kernel
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[(7 * 128 + 0) * 4 + 0] = clock64(); p.trace[(7 * 128 + 0) * 4 + 1] = gt;
   }
   if (warp == W_MMA) tmem_alloc(tmem_slot, 512u);
   tc_fence_before();
@@ -393,6 +398,10 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (p.trace && blockIdx.x == 0 && tid == 0) {
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[(7 * 128 + 0) * 4 + 2] = clock64(); p.trace[(7 * 128 + 0) * 4 + 3] = gt;
+  }
   if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512u);
@@ -500,13 +509,14 @@ int rb_variant(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols,
 }
 }  // namespace
 
-bool fused_rb_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride) {
+bool fused_dw_pw_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride) {
   return rb_variant(dw, pw, rows, cols, stride) >= 0;
 }
 
-// cudaErrorNotSupported (nothing launched) when the block has no resident-filter variant.
-cudaError_t launch_fused_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n, int rows,
-                            int cols, int stride, int pad_lo, int num_sms, cudaStream_t st, std::string* err) {
+// cudaErrorNotSupported (nothing launched) when the block has no fused variant (the filter must fit in
+// shared memory: layers 2-11; the 512- and 1024-channel blocks run as two kernels).
+cudaError_t launch_fused_dw_pw(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n, int rows,
+                               int cols, int stride, int pad_lo, int num_sms, cudaStream_t st, std::string* err) {
   const int v = rb_variant(dw, pw, rows, cols, stride);
   if (v < 0) return cudaErrorNotSupported;
   if (n <= 0) return cudaSuccess;

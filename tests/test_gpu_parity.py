@@ -356,7 +356,6 @@ def test_pipelined_forward_matches_blocking(mn, synth_net):
 
 
 @pytest.mark.parametrize("c,cout,h,stride,pad,n", [
-    (512, 512, 14, 1, 0, 3), (512, 512, 14, 1, 0, 1), (64, 256, 14, 1, 0, 2), (256, 512, 14, 1, 0, 5),
     # resident-filter kernel (fused_rb.cu): the five blocks of layers 2-11, both padding conventions
     (32, 64, 112, 1, 0, 2), (64, 128, 112, 2, 1, 2), (64, 128, 112, 2, 0, 1), (128, 128, 56, 1, 0, 3),
     (128, 256, 56, 2, 1, 3), (128, 256, 56, 2, 0, 2), (256, 256, 28, 1, 0, 5), (256, 256, 28, 1, 0, 40)])
@@ -392,6 +391,20 @@ def test_fused_dw_pw_block(mn, oracle_mod, c, cout, h, stride, pad, n):
     ctx.pointwise(out2, m, fp, ho, ho, c, cout)
     got2 = ctx.download_planar(out2)
     assert np.mean(got2 == got) > 0.999 and rel_err(got, got2) <= 2 * BF16_TOL
+    ctx.close()
+
+
+def test_fused_block_unsupported_shape(mn):
+    """blocks whose filter does not fit in shared memory report MNV1_EUNSUPPORTED and launch nothing"""
+    ctx = mn.Context(0, mn.BF16)
+    c = 512
+    fd = ctx.filter(mn.DEPTHWISE, np.ones((c, 3, 3), np.float32), c, c, None, None, mn.ACT_RELU6)
+    fp = ctx.filter(mn.POINTWISE, np.ones((c, c), np.float32), c, c, None, None, mn.ACT_RELU6)
+    x = ctx.malloc(1, c, 14, 14)
+    out = ctx.malloc(1, c, 14, 14)
+    with pytest.raises(mn.Mnv1Error) as e:
+        ctx.dw_pw_block(out, x, fd, fp, 14, 14, 1)
+    assert e.value.code == -6   # MNV1_EUNSUPPORTED
     ctx.close()
 
 
