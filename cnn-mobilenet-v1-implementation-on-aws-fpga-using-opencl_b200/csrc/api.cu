@@ -432,6 +432,10 @@ static cudaError_t run_depthwise(mnv1_ctx* ctx, void* out, const void* in, const
   ctx->launches++;
   if (ctx->dtype == MNV1_BF16 && f->w_scaled) {
     ctx->err.clear();
+    cudaError_t er = mnv1::launch_depthwise_ring((bf16*)out, (const bf16*)in, f->w_scaled, f->shift, (int)f->act, n, rows,
+                                                 cols, stride, f->cout, pad_lo_for(ctx, stride), ctx->num_sms,
+                                                 ctx->stream, &ctx->err);
+    if (er != cudaErrorNotSupported) { ctx->last_kernel = "depthwise_ring_kernel"; return er; }
     cudaError_t e = mnv1::launch_depthwise_tma((bf16*)out, (const bf16*)in, f->w_scaled, f->shift, (int)f->act, n, rows,
                                                cols, stride, f->cout, pad_lo_for(ctx, stride), ctx->num_sms,
                                                ctx->stream, &ctx->err);

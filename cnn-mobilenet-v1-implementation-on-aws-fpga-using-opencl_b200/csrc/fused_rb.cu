@@ -126,10 +126,11 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 
   // constants -> shared memory
   {
-    float* taps = reinterpret_cast<float*>(smem_g + Cfg::OFF_TAPS);
-    for (int i = tid; i < 9 * C; i += Cfg::THREADS) taps[i] = p.dw_taps[i];
+    constexpr int PER = (9 * C / 4 + Cfg::THREADS - 1) / Cfg::THREADS;
+    stage_constants<PER>(reinterpret_cast<float*>(smem_g + Cfg::OFF_TAPS), p.dw_taps, 9 * C, tid, Cfg::THREADS);
     float* ds = reinterpret_cast<float*>(smem_g + Cfg::OFF_DSH);
-    for (int i = tid; i < C; i += Cfg::THREADS) ds[i] = p.dw_shift ? p.dw_shift[i] : 0.f;
+    if (p.dw_shift) stage_constants<1>(ds, p.dw_shift, C, tid, Cfg::THREADS);
+    else for (int i = tid; i < C; i += Cfg::THREADS) ds[i] = 0.f;
   }
   if (tid == 0) {
     prefetch_tmap(&tmap_in); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_out); prefetch_tmap(&tmap_out2);

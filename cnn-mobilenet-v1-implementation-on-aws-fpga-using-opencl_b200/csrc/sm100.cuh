@@ -171,6 +171,26 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi, uint32_t cap2) {
   return d;
 }
 
+// Block-cooperative copy of a small fp32 constant array (a multiple of 4 floats, 16-byte aligned) into
+// shared memory: every thread issues ALL of its 128-bit loads before the first store, so the prologue
+// pays one global-memory latency instead of one per loop iteration (measured: 8 us of a 32 us kernel).
+template <int MAX_PER_THREAD>
+__device__ __forceinline__ void stage_constants(float* dst_smem, const float* __restrict__ src, int count, int tid,
+                                                int nthreads) {
+  float4 v[MAX_PER_THREAD];
+  const int n4 = count >> 2;
+#pragma unroll
+  for (int i = 0; i < MAX_PER_THREAD; ++i) {
+    const int k = tid + i * nthreads;
+    if (k < n4) v[i] = __ldg(reinterpret_cast<const float4*>(src) + k);
+  }
+#pragma unroll
+  for (int i = 0; i < MAX_PER_THREAD; ++i) {
+    const int k = tid + i * nthreads;
+    if (k < n4) reinterpret_cast<float4*>(dst_smem)[k] = v[i];
+  }
+}
+
 }  // namespace ptx
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
