@@ -2,6 +2,7 @@
 // points with kernel.cl's argument order, and the whole-network executor (activation arena +
 // CUDA graph) that replaces the 29 copy-pasted layer blocks of MobileNet.c:207-2763.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -19,6 +20,11 @@ int read_ppm(const char* path, uint8_t* out, int height, int width, std::string*
 }  // namespace mnv1
 
 static thread_local std::string g_last_error;
+
+bool mnv1::pdl_enabled() {
+  static const bool on = getenv("MNV1_NO_PDL") == nullptr;
+  return on;
+}
 
 struct LayerDef { int kind, cin, cout, hin, hout, stride; long w_off, w_cnt, c_off; };
 

@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mnv1.h"
@@ -71,6 +72,27 @@ __device__ __forceinline__ float bf16hi_to_f32(uint32_t p) { return __uint_as_fl
 
 // ---- launchers implemented in the .cu files (all asynchronous on `st`) -------------------
 namespace mnv1 {
+
+// Programmatic dependent launch: consecutive kernels of the layer schedule are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization.  Every kernel triggers its dependents at entry
+// (pdl_trigger) and waits for its predecessor (pdl_wait: full completion + memory flush) only after its
+// own prologue — barrier init, TMEM allocation, tensor-map prefetch, constants — so the launch latency
+// and the prologue of layer k+1 hide under the tail of layer k.  MNV1_NO_PDL=1 turns the attribute off.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 struct StemArgs {
   const uint8_t *r, *g, *b;  // plane base pointers (interleaved: g = r+1, b = r+2)

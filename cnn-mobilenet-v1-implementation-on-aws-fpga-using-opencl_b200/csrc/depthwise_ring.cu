@@ -69,6 +69,7 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap_in, const DrParam
   const uint32_t sIn = smem + Cfg::OFF_IN, sTaps = smem + Cfg::OFF_TAPS, sSh = smem + Cfg::OFF_SH;
   const uint32_t in_full = smem + Cfg::OFF_BAR, in_empty = in_full + 8u * NI;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
 
   {
     constexpr int PER = (9 * C / 4 + Cfg::THREADS - 1) / Cfg::THREADS;
@@ -83,6 +84,7 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap_in, const DrParam
     mbar_init_fence();
   }
   __syncthreads();
+  pdl_wait();                                            // the previous layer's output is complete and visible
 
   // this CTA's units: blockIdx.x, blockIdx.x + gridDim.x, ...
   const int G = gridDim.x;
@@ -237,9 +239,8 @@ cudaError_t launch_dr(bf16* out, const bf16* in, const float* taps, const float*
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (act != MNV1_ACT_NONE) depthwise_ring_kernel<Cfg, true><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tin, p);
-  else depthwise_ring_kernel<Cfg, false><<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(tin, p);
-  return cudaGetLastError();
+  if (act != MNV1_ACT_NONE) return launch_pdl(depthwise_ring_kernel<Cfg, true>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, st, tin, p);
+  return launch_pdl(depthwise_ring_kernel<Cfg, false>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, st, tin, p);
 }
 
 //                   S    C   H TWO R TW RC NG NIG

@@ -119,6 +119,7 @@ depthwise_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const DwParams
   const uint32_t bar_full = smem + (uint32_t)stages * STAGE_PITCH;   // stages x 8 bytes
   const uint32_t bar_empty = bar_full + 8u * DT_MAX_STAGES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_in) : "memory");
@@ -126,6 +127,7 @@ depthwise_tma_kernel(const __grid_constant__ CUtensorMap tmap_in, const DwParams
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();   // the previous layer's output is complete and visible
 
   // a CTA owns channel block cb and every (gridDim/cblocks)-th of the remaining items
   const int cblocks = p.cblocks;
@@ -337,8 +339,7 @@ cudaError_t launch_variant2(const bf16* in, DwParams p, int num_sms, cudaStream_
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  depthwise_tma_kernel<S, CB, TWO, TW, RC, RELU><<<(unsigned)grid, DT_THREADS, smem, st>>>(tm, p);
-  return cudaGetLastError();
+  return launch_pdl(depthwise_tma_kernel<S, CB, TWO, TW, RC, RELU>, dim3((unsigned)grid), dim3(DT_THREADS), smem, st, tm, p);
 }
 
 template <int S, int CB, int TWO, int TW, int RC>

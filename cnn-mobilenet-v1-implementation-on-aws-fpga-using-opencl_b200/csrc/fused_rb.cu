@@ -120,6 +120,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   const uint32_t tm_full = a_empty + 8u * NA, tm_empty = tm_full + 8u * NACC, b_full = tm_empty + 8u * NACC, tmem_slot = b_full + 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   // Warp roles.  The SM's issue arbiter favours the highest warp ids, so the latency-critical
   // single-thread roles and the epilogue sit above the bulk stencil workers.
   constexpr int W_EPI = NG * GW, W_MMA = W_EPI + NE * RB_EPI_WARPS, W_TMA = W_MMA + 1;
@@ -149,6 +150,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = lds32(tmem_slot);
+  pdl_wait();                                            // the previous layer's output is complete and visible
 
   // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...
   const long G = gridDim.x;
@@ -468,10 +470,12 @@ cudaError_t launch_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-#define RB_LAUNCH(A, B) fused_rb_kernel<Cfg, A, B><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(tin, pw->tmap_b, tout, tout2, p)
+  cudaError_t le;
+#define RB_LAUNCH(A, B) le = launch_pdl(fused_rb_kernel<Cfg, A, B>, dim3((unsigned)grid), dim3(Cfg::THREADS), Cfg::SMEM, st, tin, pw->tmap_b, tout, tout2, p)
   if (dr) { if (pr) RB_LAUNCH(true, true); else RB_LAUNCH(true, false); }
   else    { if (pr) RB_LAUNCH(false, true); else RB_LAUNCH(false, false); }
 #undef RB_LAUNCH
+  if (le != cudaSuccess) return le;
   if (tracing) {   // debug only: dump the stamps of the last launch
     std::vector<unsigned long long> h(8 * 128 * 4);
     cudaStreamSynchronize(st);

@@ -19,6 +19,8 @@ template <typename T, typename TO>
 __global__ void __launch_bounds__(256) pool_kernel(TO* __restrict__ out, const T* __restrict__ in, int n, int hw,
                                                    int c) {
   __shared__ float part[4][64][4];
+  pdl_trigger();
+  pdl_wait();
   const int img = blockIdx.x, q = threadIdx.x & 63, ph = threadIdx.x >> 6;
   const int c0 = blockIdx.y * 256 + q * 4;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -52,7 +54,7 @@ cudaError_t launch_pool(mnv1_dtype dt, void* out, const void* in, int n, int hw,
   if (n <= 0) return cudaSuccess;
   dim3 grid(n, (c + 255) / 256);
   if (dt == MNV1_F32) pool_kernel<float, float><<<grid, 256, 0, st>>>((float*)out, (const float*)in, n, hw, c);
-  else if (out_f32)   pool_kernel<bf16, float><<<grid, 256, 0, st>>>((float*)out, (const bf16*)in, n, hw, c);
+  else if (out_f32)   return launch_pdl(pool_kernel<bf16, float>, grid, dim3(256), 0, st, (float*)out, (const bf16*)in, n, hw, c);
   else                pool_kernel<bf16, bf16><<<grid, 256, 0, st>>>((bf16*)out, (const bf16*)in, n, hw, c);
   return cudaGetLastError();
 }
@@ -186,6 +188,8 @@ __global__ void __launch_bounds__(FCM_WARPS * 32) fc_mma_kernel(float* __restric
                                                                 int n, int k, int classes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   __shared__ float s_part[FCM_WARPS][16][FCM_NT * 8 + 1];
+  pdl_trigger();
+  pdl_wait();
   const int img0 = blockIdx.y * 16, cls0 = blockIdx.x * (FCM_NT * 8);
   const int kw = k / FCM_WARPS, k_lo = warp * kw, k_hi = k_lo + kw;   // this warp's share of the contraction
   const int r0 = min(img0 + g, n - 1), r1 = min(img0 + g + 8, n - 1);       // clamped rows are computed, never stored
@@ -255,8 +259,7 @@ cudaError_t launch_fc(float* out, const float* pooled, const float* w_f32, const
   if (smem > 96 * 1024) return cudaErrorNotSupported;
   if (w_bf16 && k % (32 * FCM_WARPS) == 0) {   // bf16 filter: tensor cores, exact fp32 activations (three bf16 pieces)
     dim3 g2((classes + FCM_NT * 8 - 1) / (FCM_NT * 8), (n + 15) / 16);
-    fc_mma_kernel<<<g2, FCM_WARPS * 32, 0, st>>>(out, pooled, w_bf16, bias, n, k, classes);
-    return cudaGetLastError();
+    return launch_pdl(fc_mma_kernel, g2, dim3(FCM_WARPS * 32), 0, st, out, pooled, w_bf16, bias, n, k, classes);
   }
   if (w_bf16) fc_kernel<bf16><<<grid, 256, smem, st>>>(out, pooled, w_bf16, bias, n, k, classes);
   else fc_kernel<float><<<grid, 256, smem, st>>>(out, pooled, w_f32, bias, n, k, classes);
@@ -272,6 +275,8 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_kernel(const float* __rest
                                                              float* __restrict__ top1_prob) {
   __shared__ float s_mx[4], s_sum[4];
   __shared__ int s_arg[4];
+  pdl_trigger();
+  pdl_wait();
   const int img = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* z = logits + (long)img * classes;
   float v[SM_PER];
@@ -354,7 +359,8 @@ __global__ void __launch_bounds__(128) softmax_warp_kernel(const float* __restri
 cudaError_t launch_softmax(const float* logits, int n, int classes, float* prob, int* top1, float* top1_prob,
                            cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  if (classes <= SM_THREADS * SM_PER) softmax_kernel<<<(unsigned)n, SM_THREADS, 0, st>>>(logits, n, classes, prob, top1, top1_prob);
+  if (classes <= SM_THREADS * SM_PER)
+    return launch_pdl(softmax_kernel, dim3((unsigned)n), dim3(SM_THREADS), 0, st, logits, n, classes, prob, top1, top1_prob);
   else softmax_warp_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(logits, n, classes, prob, top1, top1_prob);
   return cudaGetLastError();
 }

@@ -171,6 +171,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(s_shift + TC_MAX_COUT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
   const int n_tiles = Cout / BN;
   const long m_tiles = (M + TC_BM - 1) / TC_BM;
   // work unit = `group` consecutive m-tiles of one n-tile (group > 1 only when n_tiles == 1)
@@ -196,6 +197,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_wait();   // the previous layer's output is complete and visible
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -428,12 +430,13 @@ cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   const unsigned grid = (unsigned)(units < num_sms ? units : num_sms);
   const uint32_t cap2 = act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;  // bf16x2 (6, 6) or (+inf, +inf)
   const bool relu = act != MNV1_ACT_NONE;
+  cudaError_t le;
 #define PW_LAUNCH(R, B) \
-  pointwise_tc_kernel<BN, R, B><<<grid, TC_THREADS, smem, st>>>(ta, tb, to, scale, shift, cap2, m, k, cout, stages, group)
+  le = launch_pdl(pointwise_tc_kernel<BN, R, B>, dim3(grid), dim3(TC_THREADS), smem, st, ta, tb, to, scale, shift, cap2, m, k, cout, stages, group)
   if (relu) { if (resb) PW_LAUNCH(true, true); else PW_LAUNCH(true, false); }
   else      { if (resb) PW_LAUNCH(false, true); else PW_LAUNCH(false, false); }
 #undef PW_LAUNCH
-  return cudaGetLastError();
+  return le;
 }
 
 }  // namespace

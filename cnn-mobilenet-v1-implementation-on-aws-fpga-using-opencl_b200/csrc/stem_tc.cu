@@ -121,6 +121,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const StemTcParams 
   const uint32_t a_full = bars, mma_done = bars + 16, tmem_free = bars + 32;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_trigger();
   if (tid < ST_C) {
     s_scale[tid] = p.scale ? p.scale[tid] : 1.f;
     s_shift[tid] = p.shift2[tid];
@@ -147,6 +148,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmap_out, const StemTcParams 
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();   // the previous step's kernels are done with the activation arena; the images are in place
 
   const int Wo = p.ocols, HoWo = p.orows * p.ocols, W = p.cols, H = p.rows, ps = p.pix_stride;
   const long tiles = (p.m_total + 127) / 128;
@@ -407,15 +409,16 @@ cudaError_t launch_stem_tc(bf16* out, const StemArgs& a, const __half* wq_dev, c
   // interleaved = one base pointer with g = r + 1, b = r + 2 and pixel stride 3
   const bool il = a.pix_stride == 3 && a.g == a.r + 1 && a.b == a.r + 2;
   if (!il && a.pix_stride != 1) return cudaErrorNotSupported;
+  cudaError_t le = cudaSuccess;
 #define ST_LAUNCH(S, R)                                                                          \
   do {                                                                                            \
-    if (il) stem_tc_kernel<S, R, true><<<(unsigned)grid, ST_THREADS, smem, st>>>(tm, p);          \
-    else    stem_tc_kernel<S, R, false><<<(unsigned)grid, ST_THREADS, smem, st>>>(tm, p);         \
+    if (il) le = launch_pdl(stem_tc_kernel<S, R, true>, dim3((unsigned)grid), dim3(ST_THREADS), smem, st, tm, p);  \
+    else    le = launch_pdl(stem_tc_kernel<S, R, false>, dim3((unsigned)grid), dim3(ST_THREADS), smem, st, tm, p); \
   } while (0)
   if (a.stride == 2) { if (relu) ST_LAUNCH(2, true); else ST_LAUNCH(2, false); }
   else               { if (relu) ST_LAUNCH(1, true); else ST_LAUNCH(1, false); }
 #undef ST_LAUNCH
-  return cudaGetLastError();
+  return le;
 }
 
 }  // namespace mnv1
