@@ -344,7 +344,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         if (q % RC == 0) {                                   // first row of the next chunk of the unit
           prev_stage = cur_stage;
           cur_stage = (uint32_t)(g * NIG) + rstage;
-          mbar_wait(in_full + 8u * cur_stage, rphase);
+          mbar_wait_relaxed(in_full + 8u * cur_stage, rphase);
           if (q == 0 && tracer) rb_stamp(p.trace, 3 + g, ul / NG, 1);
           rowbase = sIn + cur_stage * Cfg::CHUNK_PITCH + in_off;
           if (++rstage == NIG) { rstage = 0; rphase ^= 1u; }
@@ -381,7 +381,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                                        fmaf(x[c * S + 1][v], w[3 * tr + 1][v], fmaf(x[c * S][v], w[3 * tr][v], init)));
               }
             if (tr == 2) {                                  // output row o is complete
-              if (o == 0) { mbar_wait(a_empty + 8u * ast, aph ^ 1u); if (tracer) rb_stamp(p.trace, 3 + g, ul / NG, 2); }   // the MMAs that last read this A stage retired
+              if (o == 0) { mbar_wait_relaxed(a_empty + 8u * ast, aph ^ 1u); if (tracer) rb_stamp(p.trace, 3 + g, ul / NG, 2); }   // the MMAs that last read this A stage retired
               if (active) {
 #pragma unroll
                 for (int c = 0; c < TW; ++c)

@@ -40,6 +40,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// The same wait for the bulk worker warps: a failed probe is followed by a short nanosleep, so a dozen
+// waiting warps do not burn the issue slots the working warps need (15 % of all issued instructions
+// were try_wait / branch pairs before: profiles/r01_rb_l06_v1_ncu.txt).
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBARR_DONE;\n"
+      "MBARR_WAIT:\n"
+      "nanosleep.u32 96;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra MBARR_WAIT;\n"
+      "MBARR_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
 }
