@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 
 namespace mnv1 {
 
@@ -98,6 +99,36 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The issuing warp runs its loop CONVERGED (all 32 lanes wait, compute the same descriptors) and only
+// the tcgen05 instructions are predicated on one elected lane.  Inside an `if (lane == 0)` branch every
+// operand lives in per-thread registers and each UTCHMMA is preceded by an election loop of
+// R2UR.BROADCASTs (~24 instructions, ~150 cycles): the MMAs were ISSUE-bound, 200 cycles apiece.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ void umma_bf16_if(uint32_t elected, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_if(uint32_t elected, uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(elected)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -134,6 +165,11 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi, uint32_t cap2) {
   return d;
 }
 
+// debug: SM-clock stamps of CTA 0 (MNV1_PW_TRACE=<file>): trace[role][idx][slot], 128 entries per role
+__device__ __forceinline__ void pw_stamp(unsigned long long* tr, int role, long idx, int slot) {
+  if (tr && blockIdx.x == 0 && idx < 128) tr[(role * 128 + idx) * 4 + slot] = clock64();
+}
+
 struct __align__(8) TcBarriers {
   uint64_t full[TC_MAX_STAGES];
   uint64_t empty[TC_MAX_STAGES];
@@ -150,7 +186,8 @@ template <int BN, bool RELU, bool RESB>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const float* __restrict__ scale,
-                    const float* __restrict__ shift, uint32_t cap2, long M, int K, int Cout, int stages, int group) {
+                    const float* __restrict__ shift, uint32_t cap2, long M, int K, int Cout, int stages, int group, int dbg,
+                    unsigned long long* trace) {
   constexpr uint32_t A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
   constexpr uint32_t B_BYTES = BN * TC_BK * 2;
   constexpr uint32_t STAGE_BYTES = A_BYTES + (RESB ? 0u : B_BYTES);
@@ -201,7 +238,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (lane == 0 && !(dbg & 2)) {
       if (RESB) {  // the filter is loaded once: every k-block of the single n-tile
         mbar_expect_tx(&bars->resb_full, (uint32_t)num_kb * B_BYTES);
         for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(s_resb + (size_t)kb * B_BYTES, &tmap_b, &bars->resb_full, kb * TC_BK, 0);
@@ -213,34 +250,41 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int g = 0; g < group && mt0 + g < m_tiles; ++g) {
           const int m_idx = (int)(mt0 + g) * TC_BM;
           for (int kb = 0; kb < num_kb; ++kb) {
+            if (kb == 0 && g == 0) pw_stamp(trace, 0, u / gridDim.x, 0);
             mbar_wait(&bars->empty[stage], phase ^ 1u);
             uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
             mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
             tma_load_2d(sa, &tmap_a, &bars->full[stage], kb * TC_BK, m_idx);
             if (!RESB) tma_load_2d(sa + A_BYTES, &tmap_b, &bars->full[stage], kb * TC_BK, n_idx);
+            if (kb == num_kb - 1) pw_stamp(trace, 0, u / gridDim.x, 2);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (one thread) =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+    {
       constexpr uint32_t idesc = make_idesc(BN);
+      const uint32_t elected = elect_one();
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      if (RESB) { mbar_wait(&bars->resb_full, 0); tc_fence_after(); }
+      if (RESB && !(dbg & 2)) { mbar_wait(&bars->resb_full, 0); tc_fence_after(); }
       const uint32_t resb_u = smem_u32(s_resb);
+      const uint32_t ring_u = smem_u32(smem);
       for (long u = blockIdx.x; u < num_units; u += gridDim.x) {
         const long mt0 = (u / n_tiles) * group;
+        if (elected) pw_stamp(trace, 1, u / gridDim.x, 0);
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
+        if (elected) pw_stamp(trace, 1, u / gridDim.x, 1);
         for (int g = 0; g < group && mt0 + g < m_tiles; ++g) {
           const uint32_t tmem_d = tmem_base + (uint32_t)as * ACC_COLS + (uint32_t)(g * BN);
           for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&bars->full[stage], phase);          // TMA bytes have landed
+            if (!(dbg & 2)) mbar_wait(&bars->full[stage], phase);          // TMA bytes have landed
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+            if (kb == 0 && g == 0 && elected) pw_stamp(trace, 1, u / gridDim.x, 2);
+            const uint32_t sa = ring_u + (uint32_t)stage * STAGE_BYTES;
             const uint64_t da = make_smem_desc(sa);
             const uint64_t db = make_smem_desc(RESB ? resb_u + (uint32_t)kb * B_BYTES : sa + A_BYTES);
             const int krem = K - kb * TC_BK;                // K tail: skip the zero-filled 16-wide slices
@@ -248,13 +292,14 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
             for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
               // advance 16 elements = 32 bytes inside the 128B swizzle row: +2 in the (>>4) address field
-              if (k < nk) umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+              if (k < nk) umma_bf16_if(elected, tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
             }
-            umma_commit(&bars->empty[stage]);              // frees the smem slot when these MMAs retire
+            umma_commit_if(elected, &bars->empty[stage]);  // frees the smem slot when these MMAs retire
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
         }
-        umma_commit(&bars->tmem_full[as]);                 // accumulator stage complete -> epilogue
+        umma_commit_if(elected, &bars->tmem_full[as]);     // accumulator stage complete -> epilogue
+        if (elected) pw_stamp(trace, 1, u / gridDim.x, 3);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -286,8 +331,10 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (long u = blockIdx.x; u < num_units; u += gridDim.x) {
       const long mt0 = (u / n_tiles) * group;
       const int n_idx = (int)(u % n_tiles) * BN;
+      if (threadIdx.x == 64) pw_stamp(trace, 2, u / gridDim.x, 0);
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
+      if (threadIdx.x == 64) pw_stamp(trace, 2, u / gridDim.x, 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * ACC_COLS + (uint32_t)(32 * half);
       const int nblk = group * (BN / 64);                // 64-column blocks in this accumulator stage
 #pragma unroll 1
@@ -329,6 +376,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+      if (threadIdx.x == 64) pw_stamp(trace, 2, u / gridDim.x, 2);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -430,12 +478,28 @@ cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   const unsigned grid = (unsigned)(units < num_sms ? units : num_sms);
   const uint32_t cap2 = act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;  // bf16x2 (6, 6) or (+inf, +inf)
   const bool relu = act != MNV1_ACT_NONE;
+  // debug facilities: MNV1_PW_DBG=2 runs without loads (MMAs never wait), MNV1_PW_TRACE=<file> dumps CTA 0's stamps
+  static const int dbg = getenv("MNV1_PW_DBG") ? atoi(getenv("MNV1_PW_DBG")) : 0;
+  static unsigned long long* d_trace_buf = nullptr;
+  unsigned long long* d_trace = nullptr;
+  const char* trace_path = getenv("MNV1_PW_TRACE");
+  if (trace_path) {
+    if (!d_trace_buf) cudaMalloc(&d_trace_buf, 4 * 128 * 4 * 8);
+    cudaMemsetAsync(d_trace_buf, 0, 4 * 128 * 4 * 8, st);
+    d_trace = d_trace_buf;
+  }
   cudaError_t le;
 #define PW_LAUNCH(R, B) \
-  le = launch_pdl(pointwise_tc_kernel<BN, R, B>, dim3(grid), dim3(TC_THREADS), smem, st, ta, tb, to, scale, shift, cap2, m, k, cout, stages, group)
+  le = launch_pdl(pointwise_tc_kernel<BN, R, B>, dim3(grid), dim3(TC_THREADS), smem, st, ta, tb, to, scale, shift, cap2, m, k, cout, stages, group, dbg, d_trace)
   if (relu) { if (resb) PW_LAUNCH(true, true); else PW_LAUNCH(true, false); }
   else      { if (resb) PW_LAUNCH(false, true); else PW_LAUNCH(false, false); }
 #undef PW_LAUNCH
+  if (trace_path && le == cudaSuccess) {
+    std::vector<unsigned long long> hbuf(4 * 128 * 4);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf.data(), d_trace_buf, hbuf.size() * 8, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "wb")) { fwrite(hbuf.data(), 8, hbuf.size(), f); fclose(f); }
+  }
   return le;
 }
 
