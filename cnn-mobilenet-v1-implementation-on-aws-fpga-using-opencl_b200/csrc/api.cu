@@ -455,8 +455,8 @@ static cudaError_t run_pointwise(mnv1_ctx* ctx, void* out, const void* in, const
                                  bool force_simt) {
   ctx->launches++;
   if (ctx->dtype == MNV1_BF16 && f->has_tmap && !force_simt) {
-    ctx->last_kernel = "pointwise_tc_kernel";
     ctx->err.clear();
+    ctx->last_kernel = "pointwise_tc_kernel";
     return mnv1::launch_pointwise_tc((bf16*)out, (const bf16*)in, f, m, f->cin, f->cout, ctx->num_sms,
                                      ctx->stream, &ctx->err);
   }

@@ -1,0 +1,292 @@
+// pointwise_mc.cu — the 1x1 convolution for the tensor-bound layers (Cout a multiple of 256, K >= 256:
+// layers 13-27 of the MobileNet.c schedule) as a 2-CTA cluster kernel with a MULTICAST filter.
+//
+// Same contract and arithmetic as pointwise_tc.cu (`pointwise`, kernel.cl:94-114).  What the traces
+// of that kernel showed on the 512x512 layers (profiles/r01_pw_trace.txt): the UMMAs of a 128x256x512
+// tile need 4.1 k cycles, but the tile took 6-7.5 k because its 384 KB of operands (128 KB of A, 256 KB
+// of B) arrive at ~59 B/cycle per SM, and the epilogue with shared staging and bar.syncs another 4.1 k.
+// Here two CTAs of a cluster work on two m-tiles of the SAME n-tile: each loads its own A tile and HALF
+// of the filter tile and multicasts that half into both CTAs' shared memory, so a CTA asks L2 for 256 KB
+// per tile instead of 384 KB; the epilogue warps work independently (private staging, own TMA stores,
+// scale/shift batched before the TMEM wait) and need ~2.6 k cycles per tile.
+//
+//   warp 0      TMA producer: A (128 x 64) + its half of B (128 x 64, multicast) per k-block; a slot is
+//               reused when BOTH CTAs' MMAs that read it have retired (empty barrier, 2 arrivals)
+//   warp 1      TMEM allocator + converged MMA issuer (one elected lane), tcgen05.commit multicast to the
+//               empty barriers of both CTAs
+//   warps 2-9   epilogue: two warps per TMEM lane quarter, alternate 64-column blocks
+#include <cstdio>
+#include <cstdlib>
+
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace mnv1 {
+namespace {
+
+using namespace ptx;
+
+constexpr int MC_BK = 64;
+constexpr int MC_EPI_WARPS = 8;
+constexpr int MC_THREADS = 64 + 32 * MC_EPI_WARPS;
+constexpr int MC_MAX_STAGES = 8;
+constexpr uint32_t MC_A_BYTES = 128 * 128;        // 128 rows x 64 bf16
+constexpr uint32_t MC_BH_BYTES = 128 * 128;       // half of the filter tile: 128 output channels x 64 bf16
+constexpr uint32_t MC_STAGE_BYTES = MC_A_BYTES + MC_BH_BYTES;   // per CTA: its A tile + its half of the filter tile
+constexpr uint32_t MC_ACC_COLS = 256;
+
+// debug: SM-clock stamps of CTA 0 (MNV1_PW_TRACE=<file>, tools/pw_trace.py): trace[role][idx][slot]
+__device__ __forceinline__ void pp_stamp(unsigned long long* tr, int role, long idx, int slot) {
+  if (tr && blockIdx.x == 0 && idx < 128) tr[(role * 128 + idx) * 4 + slot] = clock64();
+}
+
+struct McParams {
+  const float* scale;
+  const float* shift;
+  uint32_t cap2;
+  long M;
+  int K, Cout, stages;
+  unsigned long long* trace;
+};
+
+template <bool RELU>
+__global__ void __launch_bounds__(MC_THREADS, 1)
+pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, const McParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const smem_g = smem_raw + (smem - smem_u32(smem_raw));
+  const int stages = p.stages;
+  const uint32_t sRing = smem;
+  const uint32_t sOut = sRing + (uint32_t)stages * MC_STAGE_BYTES;          // 8 warps x 2 x 4 KB
+  const uint32_t sScale = sOut + MC_EPI_WARPS * 8192u;                      // [Cout] fp32
+  const uint32_t sShift = sScale + (uint32_t)p.Cout * 4u;
+  const uint32_t bars = sShift + (uint32_t)p.Cout * 4u;
+  const uint32_t full = bars, empty = full + 8u * MC_MAX_STAGES, tm_full = empty + 8u * MC_MAX_STAGES;
+  const uint32_t tm_empty = tm_full + 16, tmem_slot = tm_empty + 16;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  const uint32_t rank = cluster_ctarank();
+  const long cid = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int num_kb = p.K / MC_BK;
+  const int n_tiles = p.Cout / 256;
+  const long m_tiles = (p.M + 127) / 128, m_pairs = (m_tiles + 1) / 2;
+  const long num_units = m_pairs * n_tiles;     // a unit = (pair of m-tiles, n-tile); this CTA's m-tile is 2*pair + rank
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_out);
+    for (int s = 0; s < stages; ++s) { mbar_init(full + 8u * s, 1); mbar_init(empty + 8u * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tm_full + 8u * a, 1); mbar_init(tm_empty + 8u * a, 2 * MC_EPI_WARPS); }
+    mbar_init_fence();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * MC_ACC_COLS);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                             // the peer's barriers exist before anything is multicast to them
+  tc_fence_after();
+  const uint32_t tmem_base = lds32(tmem_slot);
+  pdl_wait();                                     // the previous layer's output is complete and visible
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      const uint32_t full_leader = mapa_shared(full, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (long u = cid; u < num_units; u += num_clusters) {
+        const int m_idx = (int)((u / n_tiles) * 2 + rank) * 128;
+        const int n_idx = (int)(u % n_tiles) * 256 + (int)rank * 128;     // the half of the filter tile this CTA holds
+        for (int kb = 0; kb < num_kb; ++kb) {
+          if (kb == 0) pp_stamp(p.trace, 0, u / num_clusters, 0);
+          mbar_wait(empty + 8u * stage, phase ^ 1u);       // the pair's MMAs that read this slot have retired
+          const uint32_t sa = sRing + (uint32_t)stage * MC_STAGE_BYTES;
+          if (rank == 0) mbar_expect_tx(full + 8u * stage, 2 * MC_STAGE_BYTES);   // both CTAs' bytes complete on the leader's barrier
+          tma_load_2d_pair(sa, &tmap_a, full_leader + 8u * stage, kb * MC_BK, m_idx);
+          tma_load_2d_pair(sa + MC_A_BYTES, &tmap_b, full_leader + 8u * stage, kb * MC_BK, n_idx);
+          if (kb == num_kb - 1) pp_stamp(p.trace, 0, u / num_clusters, 2);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (converged warp, one elected lane) =================
+    constexpr uint32_t idesc = umma_idesc_bf16_m256(256);
+    const uint32_t elected = rank == 0 ? elect_one() : 0u;
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    for (long u = cid; rank == 0 && u < num_units; u += num_clusters) {   // the leader issues for the pair
+      if (elected) pp_stamp(p.trace, 1, u / num_clusters, 0);
+      mbar_wait(tm_empty + 8u * as, aphase ^ 1u);          // epilogue has drained this accumulator stage
+      tc_fence_after();
+      if (elected) pp_stamp(p.trace, 1, u / num_clusters, 1);
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * MC_ACC_COLS;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full + 8u * stage, phase);
+        tc_fence_after();
+        if (kb == 0 && elected) pp_stamp(p.trace, 1, u / num_clusters, 2);
+        const uint32_t sa = sRing + (uint32_t)stage * MC_STAGE_BYTES;
+        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + MC_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < MC_BK / 16; ++k) umma_pair_if(elected, tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+        umma_commit_pair_if(elected, empty + 8u * stage);                  // frees the slot in both CTAs
+        if (++stage == stages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit_pair_if(elected, tm_full + 8u * as);                     // both CTAs' accumulators are complete
+      if (elected) pp_stamp(p.trace, 1, u / num_clusters, 3);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else {
+    // ================= epilogue warps 2..9: independent, private staging =================
+    {
+      const int et = threadIdx.x - 64, n4 = p.Cout >> 2;
+      if (et < n4) {
+        const float4 sv = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale) + et) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const float4 tv = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift) + et) : make_float4(0.f, 0.f, 0.f, 0.f);
+        reinterpret_cast<float4*>(smem_g + (sScale - smem))[et] = sv;
+        reinterpret_cast<float4*>(smem_g + (sShift - smem))[et] = tv;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * MC_EPI_WARPS) : "memory");
+    }
+    const int quarter = warp & 3;                        // TMEM lanes 32*quarter .. +31
+    const int h = (warp - 2) >> 2;                       // which 64-column blocks: b = h, h+2
+    const uint32_t wbuf = sOut + (uint32_t)(warp - 2) * 8192u;
+    const uint32_t row_off = (uint32_t)lane * 128u, row_x = (uint32_t)(lane & 7);
+    const uint32_t tm_empty_leader = mapa_shared(tm_empty, 0);
+    int as = 0; uint32_t aphase = 0;
+    uint32_t blk = 0;
+    for (long u = cid; u < num_units; u += num_clusters) {
+      const int m_idx = (int)((u / n_tiles) * 2 + rank) * 128 + quarter * 32;
+      const int n_idx = (int)(u % n_tiles) * 256;
+      if (threadIdx.x == 64) pp_stamp(p.trace, 2, u / num_clusters, 0);
+      mbar_wait(tm_full + 8u * as, aphase);
+      tc_fence_after();
+      if (threadIdx.x == 64) pp_stamp(p.trace, 2, u / num_clusters, 1);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * MC_ACC_COLS;
+#pragma unroll 1
+      for (int b = h; b < 4; b += 2) {
+        const uint32_t sbuf = wbuf + (blk & 1u) * 4096u;
+        ++blk;
+        uint32_t v[32];
+        tmem_ld32_nowait(taddr + (uint32_t)(b * 64), v);
+        if (lane == 0) tma_store_wait_read<1>();           // the store issued two blocks ago has consumed this buffer
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          // this half's 32 scale / shift values first: their latency hides under the TMEM load
+          const uint32_t col = (uint32_t)(n_idx + b * 64 + 32 * half);
+          float4 s4[8], t4[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s4[j] = lds128f(sScale + (col + 4 * j) * 4u); t4[j] = lds128f(sShift + (col + 4 * j) * 4u); }
+          tmem_ld_wait();
+          uint32_t q[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            q[2 * j] = pack2<RELU>(fmaf(__uint_as_float(v[4 * j + 0]), s4[j].x, t4[j].x), fmaf(__uint_as_float(v[4 * j + 1]), s4[j].y, t4[j].y), p.cap2);
+            q[2 * j + 1] = pack2<RELU>(fmaf(__uint_as_float(v[4 * j + 2]), s4[j].z, t4[j].z), fmaf(__uint_as_float(v[4 * j + 3]), s4[j].w, t4[j].w), p.cap2);
+          }
+          if (half == 0) tmem_ld32_nowait(taddr + (uint32_t)(b * 64 + 32), v);   // second half under the stores
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            sts128(sbuf + row_off + (((uint32_t)(4 * half + c4) ^ row_x) << 4), q[4 * c4], q[4 * c4 + 1], q[4 * c4 + 2], q[4 * c4 + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {   // box = 64 columns x 32 rows; rows past M are clipped by the TMA unit
+          tma_store_2d(&tmap_out, sbuf, n_idx + b * 64, m_idx);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tm_empty_leader + 8u * as);
+      if (threadIdx.x == 64) pp_stamp(p.trace, 2, u / num_clusters, 2);
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // the peer may still multicast into this CTA's ring / arrive on its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 2 * MC_ACC_COLS);
+  }
+}
+
+cudaError_t encode_box(CUtensorMap* map, const void* base, uint64_t rows, uint64_t k, uint32_t box_rows, std::string* err) {
+  EncodeTiledFn fn = tensor_map_encoder();
+  if (!fn) { if (err) *err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
+  cuuint64_t gdim[2] = {k, rows};
+  cuuint64_t gstride[1] = {k * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { if (err) *err = "pointwise_pair: tensor map encode failed"; return cudaErrorInvalidValue; }
+  return cudaSuccess;
+}
+
+}  // namespace
+
+// cudaErrorNotSupported (nothing launched) when the shape has no cluster variant.
+cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* f, long m, int k, int cout, int num_sms,
+                                cudaStream_t st, std::string* err) {
+  static const bool off = getenv("MNV1_NO_PAIR") != nullptr;   // debug switch: fall back to pointwise_tc_kernel
+  if (off || !f->w_bf16 || cout % 256 || k % MC_BK || k < 256 || cout > 1024 || num_sms < 2) return cudaErrorNotSupported;
+  if (m <= 0) return cudaSuccess;
+  CUtensorMap ta, tb, to;
+  cudaError_t e = encode_box(&ta, in, (uint64_t)m, (uint64_t)k, 128, err);
+  if (e == cudaSuccess) e = encode_box(&tb, f->w_bf16, (uint64_t)cout, (uint64_t)k, 128, err);
+  if (e == cudaSuccess) e = encode_box(&to, out, (uint64_t)m, (uint64_t)cout, 32, err);
+  if (e != cudaSuccess) return e;
+  const size_t fixed = 1024 + MC_EPI_WARPS * 8192 + (size_t)cout * 8 + 16 * MC_MAX_STAGES + 64;
+  int stages = (int)((227 * 1024 - fixed) / MC_STAGE_BYTES);
+  if (stages > MC_MAX_STAGES) stages = MC_MAX_STAGES;
+  if (stages < 2) return cudaErrorNotSupported;
+  const size_t smem = fixed + (size_t)stages * MC_STAGE_BYTES;
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(pointwise_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(pointwise_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  McParams p{};
+  p.scale = f->scale; p.shift = f->shift;
+  p.cap2 = f->act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
+  p.M = m; p.K = k; p.Cout = cout; p.stages = stages;
+  static unsigned long long* d_trace_buf = nullptr;
+  const char* trace_path = getenv("MNV1_PW_TRACE");
+  if (trace_path) {
+    if (!d_trace_buf) cudaMalloc(&d_trace_buf, 4 * 128 * 4 * 8);
+    cudaMemsetAsync(d_trace_buf, 0, 4 * 128 * 4 * 8, st);
+    p.trace = d_trace_buf;
+  }
+  const long m_tiles = (m + 127) / 128, units = ((m_tiles + 1) / 2) * (cout / 256);
+  long clusters = num_sms / 2;
+  if (clusters > units) clusters = units;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * clusters));
+  cfg.blockDim = dim3(MC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  e = f->act != MNV1_ACT_NONE ? cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<true>, ta, tb, to, p)
+                              : cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<false>, ta, tb, to, p);
+  if (trace_path && e == cudaSuccess) {   // debug only: dump the stamps of this launch
+    std::vector<unsigned long long> hbuf(4 * 128 * 4);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hbuf.data(), d_trace_buf, hbuf.size() * 8, cudaMemcpyDeviceToHost);
+    if (FILE* fp = fopen(trace_path, "wb")) { fwrite(hbuf.data(), 8, hbuf.size(), fp); fclose(fp); }
+  }
+  return e;
+}
+
+}  // namespace mnv1
