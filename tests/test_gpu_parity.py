@@ -408,6 +408,19 @@ def test_fused_block_unsupported_shape(mn):
     ctx.close()
 
 
+def test_fused_layers_report(mn, synth_net):
+    """mnv1_fused_layers: a bf16 context fuses layers 2-11 pairwise inside mnv1_forward, an fp32 context nothing"""
+    c = _net_ctx(mn, mn.BF16, synth_net)
+    f = c.fused_layers()
+    assert [i + 1 for i in range(29) if f[i]] == [2, 4, 6, 8, 10]
+    c.use_fused_blocks(False)
+    assert not c.fused_layers().any()
+    c.close()
+    c32 = _net_ctx(mn, mn.F32, synth_net)
+    assert not c32.fused_layers().any()
+    c32.close()
+
+
 def test_fused_and_unfused_network_agree(mn, synth_net):
     from mnv1_b200 import synth
     c = _net_ctx(mn, mn.BF16, synth_net)

@@ -119,3 +119,48 @@ def test_bf16_storage_weights():
     assert np.max(np.abs(pw - w[L[2].w_off:L[2].w_off + L[2].w_cnt]) / np.abs(w[L[2].w_off:L[2].w_off + L[2].w_cnt])) <= 2 ** -8
     st = slice(L[0].w_off, L[0].w_off + L[0].w_cnt)  # stem: fp16 (11 significant bits) after folding 1/127.5
     assert np.max(np.abs(q[st] - w[st])) <= 2.0 ** -11 * np.max(np.abs(w[st]))
+
+
+# --------------------------------------------------------------------------- tools/compare_logs.py, bench rows
+def _load_tool(name):
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location(name, os.path.join(root, "tools" if name != "bench" else "", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_compare_logs_parses_reference_format():
+    """the reference's printf formats (MobileNet.c:315, :2792) and the per-layer / class comparison"""
+    cl = _load_tool("compare_logs")
+    ref = ("Kernel Execution time for Layer 1: 0.002000\nKernel Execution time for Layer 2: 0.004000\n"
+           "Highest Probability of the element is present at location 283 and it's value is 0.913000.\n")
+    ours = ("Kernel Execution time for Layer 1: 0.000100\nLayer 2 op: 1\t\nKernel Execution time for Layer 2: 0.000100\n"
+            "Total kernel time for 2 layer(s), batch 1: 0.000200\n"
+            "Highest Probability of the element is present at location 283 and it's value is 0.912700.\n")
+    res = cl.compare(ref, ours)
+    assert [r[0] for r in res["rows"]] == [1, 2]
+    assert abs(res["rows"][0][3] - 20.0) < 1e-9 and abs(res["rows"][1][3] - 40.0) < 1e-9
+    assert res["ref_final"] == (283, 0.913) and res["our_final"][0] == 283 and res["same_class"] is True
+    assert cl.compare(ref, ours.replace("location 283", "location 7"))["same_class"] is False
+    assert cl.compare("", "garbage")["rows"] == [] and cl.parse("nothing")[1] is None
+
+
+def test_bench_merges_fused_rows():
+    """a fused depthwise->pointwise launch is ONE roofline row: dw input + pw output + both filters"""
+    bench = _load_tool("bench")
+    from mnv1_b200.layers import LAYERS
+    peaks = {"hbm_gbs": 6543.1, "bf16_tflops": 1395.8}
+    times = [0.1] * 29
+    plain = bench.layer_roofline(LAYERS, times, 256, peaks)
+    fused = [0] * 29
+    fused[1] = 1            # layer 2 (dw) runs fused with layer 3 (pw)
+    merged = bench.layer_roofline(LAYERS, times, 256, peaks, fused)
+    assert len(plain) == 29 and len(merged) == 28
+    row = merged[1]
+    assert row["kind"] == "dw+pw" and row["layer"] == "2+3" and abs(row["us"] - 200.0) < 1e-6
+    want = (LAYERS[1].in_elems * 2 + LAYERS[2].out_elems * 2) * 256 + LAYERS[1].w_cnt * 4 + LAYERS[2].w_cnt * 2
+    assert row["bytes"] == want and row["bytes"] < plain[1]["bytes"] + plain[2]["bytes"]
+    assert abs(row["flops"] - (plain[1]["flops"] + plain[2]["flops"])) < 1.0
