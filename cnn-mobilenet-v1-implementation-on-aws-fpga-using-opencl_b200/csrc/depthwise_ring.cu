@@ -142,21 +142,21 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap_in, const DrParam
     const uint32_t img = tile / PER_IMG, rem = tile - img * PER_IMG;
     const uint32_t band = rem / Cfg::STRIPS, strip = rem - band * Cfg::STRIPS;
     // this k-block's taps and shift for the thread's 4 channels
-    float w[9][4], sh[4];
+    f32x2 w[9][2], sh[2];                                   // the thread's 4 channels as two packed fp32 pairs
     {
       const uint32_t ch = (kb * 64u + (uint32_t)quad * 4u) * 4u;
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
         const float4 a = lds128f(sTaps + (uint32_t)k * C * 4u + ch);
-        w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+        w[k][0] = f2_pack(a.x, a.y); w[k][1] = f2_pack(a.z, a.w);
       }
       const float4 a = lds128f(sSh + ch);
-      sh[0] = a.x; sh[1] = a.y; sh[2] = a.z; sh[3] = a.w;
+      sh[0] = f2_pack(a.x, a.y); sh[1] = f2_pack(a.z, a.w);
     }
     uint8_t* const obase = reinterpret_cast<uint8_t*>(p.out) +
         ((((size_t)img * HO + band * R) * WO + strip * TWO + (uint32_t)(pg * TW)) * C + kb * 64u + (uint32_t)quad * 4u) * 2u;
 
-    float acc[RING][TW][4];
+    f32x2 acc[RING][TW][2];
     uint32_t rowbase = 0, cur_stage = 0, prev_stage = 0;
     uint2 nraw[NCOL];
     auto fetch_row = [&](int q) {                          // q is a compile-time constant at every call site
@@ -173,12 +173,9 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap_in, const DrParam
     fetch_row(0);
 #pragma unroll
     for (int q = 0; q < HR; ++q) {
-      float x[NCOL][4];
+      f32x2 x[NCOL][2];
 #pragma unroll
-      for (int j = 0; j < NCOL; ++j) {
-        x[j][0] = bf16lo_to_f32(nraw[j].x); x[j][1] = bf16hi_to_f32(nraw[j].x);
-        x[j][2] = bf16lo_to_f32(nraw[j].y); x[j][3] = bf16hi_to_f32(nraw[j].y);
-      }
+      for (int j = 0; j < NCOL; ++j) { x[j][0] = f2_from_bf16x2(nraw[j].x); x[j][1] = f2_from_bf16x2(nraw[j].y); }
       if (q + 1 < HR) fetch_row(q + 1);
       if (q % RC == RC - 1 || q == HR - 1) {              // row q was the last of its chunk: hand the stage back
         __syncwarp();
@@ -193,16 +190,16 @@ depthwise_ring_kernel(const __grid_constant__ CUtensorMap tmap_in, const DrParam
 #pragma unroll
           for (int c = 0; c < TW; ++c)
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              const float init = tr == 0 ? sh[v] : acc[slot][c][v];
-              acc[slot][c][v] = fmaf(x[c * S + 2][v], w[3 * tr + 2][v],
-                                     fmaf(x[c * S + 1][v], w[3 * tr + 1][v], fmaf(x[c * S][v], w[3 * tr][v], init)));
+            for (int v = 0; v < 2; ++v) {   // FFMA2: two channels per instruction
+              const f32x2 init = tr == 0 ? sh[v] : acc[slot][c][v];
+              acc[slot][c][v] = f2_fma(x[c * S + 2][v], w[3 * tr + 2][v],
+                                     f2_fma(x[c * S + 1][v], w[3 * tr + 1][v], f2_fma(x[c * S][v], w[3 * tr][v], init)));
             }
           if (tr == 2 && active) {                          // output row o is complete
 #pragma unroll
             for (int c = 0; c < TW; ++c) {
-              const uint32_t lo = pack2<RELU>(acc[slot][c][0], acc[slot][c][1], p.cap2);
-              const uint32_t hi = pack2<RELU>(acc[slot][c][2], acc[slot][c][3], p.cap2);
+              const uint32_t lo = pack2_f2<RELU>(acc[slot][c][0], p.cap2);
+              const uint32_t hi = pack2_f2<RELU>(acc[slot][c][1], p.cap2);
               asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(obase + (size_t)(o * WO + c) * C * 2u), "r"(lo), "r"(hi) : "memory");
             }
           }

@@ -311,16 +311,16 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       const uint32_t x = (uint32_t)(pg * TW + c);
       a_off[c] = x * 128u + ((((uint32_t)quad >> 1) ^ (x & 7u)) << 4) + ((uint32_t)quad & 1u) * 8u;
     }
-    float w[9][4], sh[4];
+    f32x2 w[9][2], sh[2];                                   // the thread's 4 channels as two packed fp32 pairs
     auto load_taps = [&](int kb) {
       const uint32_t ch = (uint32_t)(kb * CK + quad * 4) * 4u;
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
         const float4 a = lds128f(sTaps + (uint32_t)k * C * 4u + ch);
-        w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+        w[k][0] = f2_pack(a.x, a.y); w[k][1] = f2_pack(a.z, a.w);
       }
       const float4 a = lds128f(sDsh + ch);
-      sh[0] = a.x; sh[1] = a.y; sh[2] = a.z; sh[3] = a.w;
+      sh[0] = f2_pack(a.x, a.y); sh[1] = f2_pack(a.z, a.w);
     };
     if (NKB == 1) load_taps(0);
     uint32_t rstage = 0, rphase = 0;                      // position in the group's private chunk ring
@@ -335,7 +335,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 
       const bool tracer = t == 0;
       if (tracer) rb_stamp(p.trace, 3 + g, ul / NG, 0);
-      float acc[RING][TW][4];
+      f32x2 acc[RING][TW][2];
       // The raw bf16 quads of input row q+1 are fetched while row q is being computed (one row of
       // software pipelining: without it every row exposes the ld.shared latency to its FFMAs).
       uint32_t rowbase = 0, cur_stage = 0, prev_stage = 0;
@@ -355,12 +355,9 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       fetch_row(0);
 #pragma unroll
       for (int q = 0; q < HR; ++q) {
-        float x[NCOL][4];
+        f32x2 x[NCOL][2];
 #pragma unroll
-        for (int j = 0; j < NCOL; ++j) {
-          x[j][0] = bf16lo_to_f32(nraw[j].x); x[j][1] = bf16hi_to_f32(nraw[j].x);
-          x[j][2] = bf16lo_to_f32(nraw[j].y); x[j][3] = bf16hi_to_f32(nraw[j].y);
-        }
+        for (int j = 0; j < NCOL; ++j) { x[j][0] = f2_from_bf16x2(nraw[j].x); x[j][1] = f2_from_bf16x2(nraw[j].y); }
         if (q + 1 < HR) fetch_row(q + 1);
         if (q % RC == RC - 1 || q == HR - 1) {              // row q was the last of its chunk: hand the stage back
           __syncwarp();
@@ -375,18 +372,18 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 #pragma unroll
             for (int c = 0; c < TW; ++c)
 #pragma unroll
-              for (int v = 0; v < 4; ++v) {
-                const float init = tr == 0 ? sh[v] : acc[slot][c][v];
-                acc[slot][c][v] = fmaf(x[c * S + 2][v], w[3 * tr + 2][v],
-                                       fmaf(x[c * S + 1][v], w[3 * tr + 1][v], fmaf(x[c * S][v], w[3 * tr][v], init)));
+              for (int v = 0; v < 2; ++v) {   // FFMA2: two channels per instruction
+                const f32x2 init = tr == 0 ? sh[v] : acc[slot][c][v];
+                acc[slot][c][v] = f2_fma(x[c * S + 2][v], w[3 * tr + 2][v],
+                                       f2_fma(x[c * S + 1][v], w[3 * tr + 1][v], f2_fma(x[c * S][v], w[3 * tr][v], init)));
               }
             if (tr == 2) {                                  // output row o is complete
               if (o == 0) { mbar_wait_relaxed(a_empty + 8u * ast, aph ^ 1u); if (tracer) rb_stamp(p.trace, 3 + g, ul / NG, 2); }   // the MMAs that last read this A stage retired
               if (active) {
 #pragma unroll
                 for (int c = 0; c < TW; ++c)
-                  sts64(dstA + a_off[c] + (uint32_t)(o * RB_TP) * 128u, pack2<DW_RELU>(acc[slot][c][0], acc[slot][c][1], p.dw_cap2),
-                        pack2<DW_RELU>(acc[slot][c][2], acc[slot][c][3], p.dw_cap2));
+                  sts64(dstA + a_off[c] + (uint32_t)(o * RB_TP) * 128u, pack2_f2<DW_RELU>(acc[slot][c][0], p.dw_cap2),
+                        pack2_f2<DW_RELU>(acc[slot][c][1], p.dw_cap2));
               }
             }
           }

@@ -177,6 +177,31 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+// Packed fp32 pairs (sm_100 FFMA2): one instruction, two IEEE fused multiply-adds — the same bits as two
+// fmaf() calls at half the issue slots.  The stencils are issue-bound with FFMA at ~55 % of their
+// instructions (profiles/r01_rb_l06_v1_ncu.txt); measured: 128 lane-FMA/clk/SM either way, 2 instead of 4
+// warp instructions per clock.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// a packed bf16 pair (one 32-bit word of the feature map) -> packed fp32 pair, exact
+__device__ __forceinline__ f32x2 f2_from_bf16x2(uint32_t p) {
+  return f2_pack(__uint_as_float(p << 16), __uint_as_float(p & 0xffff0000u));
+}
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack2_f2(f32x2 v, uint32_t cap2);
+
 // fp32 pair -> bf16x2 with ReLU folded into the convert and the upper clamp applied on the packed
 // pair (min.bf16x2): rounding is monotonic and the cap is exactly representable, so this equals
 // round(min(max(x, 0), cap)).
@@ -315,6 +340,13 @@ __device__ __forceinline__ void stage_constants(float* dst_smem, const float* __
     const int k = tid + i * nthreads;
     if (k < n4) reinterpret_cast<float4*>(dst_smem)[k] = v[i];
   }
+}
+
+template <bool RELU>
+__device__ __forceinline__ uint32_t pack2_f2(f32x2 v, uint32_t cap2) {
+  float lo, hi;
+  f2_unpack(v, lo, hi);
+  return pack2<RELU>(lo, hi, cap2);
 }
 
 }  // namespace ptx
