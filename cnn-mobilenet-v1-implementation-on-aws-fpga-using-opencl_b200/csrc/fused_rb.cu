@@ -266,8 +266,10 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const int col = b * 64 + half * 32 + j;
-              q[j / 2] = pack2<PW_RELU>(fmaf(__uint_as_float(v[j]), p.pw_scale[col], p.pw_shift[col]),
-                                        fmaf(__uint_as_float(v[j + 1]), p.pw_scale[col + 1], p.pw_shift[col + 1]), p.pw_cap2);
+              // one FFMA2 per output pair: scale / shift pairs straight from the constant bank
+              const f32x2 acc2 = f2_pack(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+              q[j / 2] = pack2_f2<PW_RELU>(f2_fma(acc2, f2_pack(p.pw_scale[col], p.pw_scale[col + 1]),
+                                                  f2_pack(p.pw_shift[col], p.pw_shift[col + 1])), p.pw_cap2);
             }
             if (half == 0) tmem_ld32_nowait(taddr + 32u, v);   // v is free again: fetch the second half under the stores
 #pragma unroll
