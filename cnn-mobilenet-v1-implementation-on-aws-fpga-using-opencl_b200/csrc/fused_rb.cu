@@ -485,7 +485,7 @@ cudaError_t launch_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
 }
 
 //                   S  CK NKB COUT TWO R TW  RC NG GW NIG NA NE NSTG
-using CfgL02 = RbCfg<1, 32, 1,  64, 16, 8, 1, 10, 2, 4, 3, 4, 2, 2>;   // 112x112x32  -> 112x112x64
+using CfgL02 = RbCfg<1, 32, 1,  64, 16, 8, 2, 10, 4, 2, 2, 4, 2, 1>;   // 112x112x32  -> 112x112x64
 using CfgL04 = RbCfg<2, 64, 1, 128, 14, 8, 2,  2, 3, 4, 5, 3, 1, 2>;   // 112x112x64  -> 56x56x128
 using CfgL06 = RbCfg<1, 64, 2, 128, 14, 8, 2,  5, 3, 4, 3, 3, 1, 2>;   // 56x56x128   -> 56x56x128
 using CfgL08 = RbCfg<2, 64, 2, 256, 14, 7, 2,  2, 3, 4, 4, 3, 1, 1>;   // 56x56x128   -> 28x28x256
