@@ -413,7 +413,7 @@ static int prepare_stem(mnv1_ctx* ctx, mnv1_filter* f) {
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   CK(ctx, mnv1::stem_tc_prepare(f->h_w.data(), f->h_scale.empty() ? nullptr : f->h_scale.data(),
                                 f->h_shift.empty() ? nullptr : f->h_shift.data(), ctx->in_scale, ctx->in_bias, f->wq,
-                                f->shift2, &f->p0));
+                                f->shift2, &f->p0, f->h_shift2));
   f->prep_scale = ctx->in_scale; f->prep_bias = ctx->in_bias; f->prepared = true;
   return MNV1_OK;
 }
@@ -426,6 +426,11 @@ static cudaError_t run_stem(mnv1_ctx* ctx, void* out, const uint8_t* r, const ui
   ctx->launches++;
   if (ctx->dtype == MNV1_BF16 && f->prepared && f->prep_scale == ctx->in_scale && f->prep_bias == ctx->in_bias) {
     ctx->err.clear();
+    if (!getenv("MNV1_NO_STEM_ROWS")) {
+      cudaError_t er = mnv1::launch_stem_rows((bf16*)out, a, f->wq, f->h_scale.empty() ? nullptr : f->h_scale.data(),
+                                              f->h_shift2, f->p0, (int)f->act, ctx->num_sms, ctx->stream, &ctx->err);
+      if (er != cudaErrorNotSupported) { ctx->last_kernel = "stem_rows_kernel"; return er; }
+    }
     cudaError_t e = mnv1::launch_stem_tc((bf16*)out, a, f->wq, f->scale, f->shift2, f->p0, (int)f->act, ctx->num_sms,
                                          ctx->stream, &ctx->err);
     if (e != cudaErrorNotSupported) { ctx->last_kernel = "stem_tc_kernel"; return e; }

@@ -36,6 +36,7 @@ struct mnv1_filter {
   std::vector<float> h_w, h_scale, h_shift;
   __half* wq = nullptr;
   float* shift2 = nullptr;
+  float h_shift2[32] = {};  // host copy of shift2 (constant-bank epilogue of stem_rows.cu)
   float prep_scale = 0.f, prep_bias = 0.f, p0 = 0.f;
   bool prepared = false;
   CUtensorMap tmap_b;       // TMA descriptor of w_bf16 (pointwise, bf16 contexts)
@@ -104,7 +105,11 @@ struct StemArgs {
 cudaError_t launch_stem(mnv1_dtype dt, void* out, const StemArgs& a, const float* w27xC,
                         Epilogue ep, cudaStream_t st);
 cudaError_t stem_tc_prepare(const float* w_oihw_host, const float* scale_host, const float* shift_host,
-                            float in_scale, float in_bias, __half* wq_dev, float* shift2_dev, float* p0_out);
+                            float in_scale, float in_bias, __half* wq_dev, float* shift2_dev, float* p0_out,
+                            float* shift2_host_out = nullptr);
+cudaError_t launch_stem_rows(bf16* out, const StemArgs& a, const __half* wq_dev, const float* scale_host,
+                             const float* shift2_host, float p0, int act, int num_sms, cudaStream_t st,
+                             std::string* err);
 cudaError_t launch_stem_tc(bf16* out, const StemArgs& a, const __half* wq_dev, const float* scale_dev,
                            const float* shift2_dev, float p0, int act, int num_sms, cudaStream_t st,
                            std::string* err);

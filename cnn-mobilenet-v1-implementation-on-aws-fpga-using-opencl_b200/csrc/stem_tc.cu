@@ -341,7 +341,8 @@ EncodeTiledFn get_encode_fn() {
 // Host-side preparation of the fp16 filter bank and folded shift for a given input transform.
 // wq_dev: [32][32] fp16, shift2_dev: [32] fp32 (both device, caller-allocated).
 cudaError_t stem_tc_prepare(const float* w_oihw_host, const float* scale_host, const float* shift_host,
-                            float in_scale, float in_bias, __half* wq_dev, float* shift2_dev, float* p0_out) {
+                            float in_scale, float in_bias, __half* wq_dev, float* shift2_dev, float* p0_out,
+                            float* shift2_host_out) {
   if (in_scale == 0.f) return cudaErrorInvalidValue;
   const float p0 = -in_bias / in_scale;
   const float p0h = __half2float(__float2half_rn(p0));
@@ -360,6 +361,7 @@ cudaError_t stem_tc_prepare(const float* w_oihw_host, const float* scale_host, c
   cudaError_t e = cudaMemcpy(wq_dev, wq, sizeof wq, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(shift2_dev, shift2, sizeof shift2, cudaMemcpyHostToDevice);
   if (p0_out) *p0_out = p0h;
+  if (shift2_host_out) for (int o = 0; o < 32; ++o) shift2_host_out[o] = shift2[o];
   return e;
 }
 
