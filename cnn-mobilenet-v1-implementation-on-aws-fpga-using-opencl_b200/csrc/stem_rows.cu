@@ -148,10 +148,10 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
           const uint32_t w0 = lds32(base + r * RB), w1 = lds32(base + r * RB + 4), w2 = lds32(base + r * RB + 8);
           const uint32_t b0 = __funnelshift_r(w0, w1, sh8), b1 = __funnelshift_r(w1, w2, sh8);
           e8[r] = (w2 >> sh8) & 0xffu;
-          a[4 * r + 0] = unbias(__byte_perm(b0, bias2, 0x4140), bias2);
-          a[4 * r + 1] = unbias(__byte_perm(b0, bias2, 0x4342), bias2);
-          a[4 * r + 2] = unbias(__byte_perm(b1, bias2, 0x4140), bias2);
-          a[4 * r + 3] = unbias(__byte_perm(b1, bias2, 0x4342), bias2);
+          a[4 * r + 0] = unbias(__byte_perm(b0, bias2, 0x5150), bias2);
+          a[4 * r + 1] = unbias(__byte_perm(b0, bias2, 0x5352), bias2);
+          a[4 * r + 2] = unbias(__byte_perm(b1, bias2, 0x5150), bias2);
+          a[4 * r + 3] = unbias(__byte_perm(b1, bias2, 0x5352), bias2);
         }
         a[12] = unbias(e8[0] | (e8[1] << 16) | bias2, bias2);
         a[13] = unbias(e8[2] | bias1, bias1);

@@ -170,13 +170,52 @@ def test_stem_layer(ctx, mn, oracle_mod, pad):
     ctx.convolute_rgb(out, rgb, f, 224, 224, 3, 2, 32)
     got = ctx.download_planar(out)
     assert rel_err(got, want) <= _tol(ctx, mn)
+    if ctx.dtype == mn.BF16:
+        assert ctx.last_kernel_name == "stem_rows_kernel"   # row-staged tcgen05 stem, not the gather fallback
     # the reference's own calling convention: three separate planes (MobileNet.c:218-246)
     planes = [ctx.upload_u8(np.ascontiguousarray(img[..., k])) for k in range(3)]
     out2 = ctx.malloc(n, 32, 112, 112)
     ctx.convolute(out2, planes[0], planes[1], planes[2], f, 224, 224, 3, 2, 32)
-    assert np.array_equal(ctx.download_planar(out2), got)
+    got2 = ctx.download_planar(out2)
+    # planar and interleaved inputs run different kernels with different K orders inside the MMA:
+    # same oracle tolerance, and at most a bf16 ulp apart from each other
+    assert rel_err(got2, want) <= _tol(ctx, mn)
+    assert rel_err(got2, got) <= _tol(ctx, mn)
+    if ctx.dtype == mn.BF16:
+        assert ctx.last_kernel_name == "stem_tc_kernel"
     ctx.set_pad_mode(mn.PAD_REF)
     ctx.set_input_transform(1.0, 0.0)
+
+
+@pytest.mark.parametrize("rows,cols,n,kernel", [(32, 32, 3, "stem_rows_kernel"), (18, 96, 2, "stem_rows_kernel"),
+                                                (64, 256, 5, "stem_rows_kernel"), (20, 40, 2, "stem_tc_kernel")])
+@pytest.mark.parametrize("pad", [0, 1])
+def test_stem_other_geometries(ctx, mn, oracle_mod, pad, rows, cols, n, kernel):
+    """Row-staged stem on other image sizes (one CTA tile = one output row, ragged tile counts), and
+    the gather kernel when a row is not a multiple of 16 bytes."""
+    rng = np.random.default_rng(31 + rows + cols)
+    img = rng.integers(0, 256, (n, rows, cols, 3), dtype=np.uint8)
+    w = (rng.standard_normal((32, 3, 3, 3)) * np.sqrt(2.0 / 27)).astype(np.float32)
+    sc = (0.5 + rng.random(32)).astype(np.float32)
+    sh = (rng.standard_normal(32) * 0.1).astype(np.float32)
+    wo = w
+    if ctx.dtype == mn.BF16:
+        wo = ((w * np.float32(1 / 127.5)).astype(np.float16).astype(np.float32) / np.float32(1 / 127.5))
+    want = oracle_mod.convolute(img, img.reshape(-1)[1:], img.reshape(-1)[2:], wo, n, rows, cols, 2, 32, pad_mode=pad,
+                                in_scale=1 / 127.5, in_bias=-1.0, scale=sc, shift=sh, act=oracle_mod.ACT_RELU6,
+                                rbf16=ctx.dtype == mn.BF16, pix_stride=3, img_stride=rows * cols * 3)
+    ctx.set_pad_mode(pad)
+    ctx.set_input_transform(1 / 127.5, -1.0)
+    try:
+        f = ctx.filter(mn.CONVOLUTE, w, 3, 32, sc, sh, mn.ACT_RELU6)
+        out = ctx.malloc(n, 32, rows // 2, cols // 2)
+        ctx.convolute_rgb(out, ctx.upload_u8(img), f, rows, cols, 3, 2, 32)
+        assert rel_err(ctx.download_planar(out), want) <= _tol(ctx, mn)
+        if ctx.dtype == mn.BF16:
+            assert ctx.last_kernel_name == kernel
+    finally:
+        ctx.set_pad_mode(mn.PAD_REF)
+        ctx.set_input_transform(1.0, 0.0)
 
 
 def test_pool_fc_softmax(ctx, mn, oracle_mod):
