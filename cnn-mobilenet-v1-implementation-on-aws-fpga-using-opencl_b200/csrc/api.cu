@@ -443,6 +443,11 @@ static cudaError_t run_depthwise(mnv1_ctx* ctx, void* out, const void* in, const
   ctx->launches++;
   if (ctx->dtype == MNV1_BF16 && f->w_scaled) {
     ctx->err.clear();
+    if (!getenv("MNV1_NO_CW")) {
+      cudaError_t ec = mnv1::launch_depthwise_cw((bf16*)out, (const bf16*)in, f->w_scaled, f->shift, (int)f->act, n, rows,
+                                                 cols, stride, f->cout, pad_lo_for(ctx, stride), ctx->stream);
+      if (ec != cudaErrorNotSupported) { ctx->last_kernel = "depthwise_cw_kernel"; return ec; }
+    }
     cudaError_t er = mnv1::launch_depthwise_ring((bf16*)out, (const bf16*)in, f->w_scaled, f->shift, (int)f->act, n, rows,
                                                  cols, stride, f->cout, pad_lo_for(ctx, stride), ctx->num_sms,
                                                  ctx->stream, &ctx->err);

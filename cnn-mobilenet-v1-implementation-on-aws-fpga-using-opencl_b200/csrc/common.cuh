@@ -124,6 +124,9 @@ cudaError_t launch_depthwise_tma(bf16* out, const bf16* in, const float* w9xC_sc
 cudaError_t launch_depthwise_ring(bf16* out, const bf16* in, const float* w9xC_scaled, const float* shift, int act, int n,
                                   int rows, int cols, int stride, int c, int pad_lo, int num_sms, cudaStream_t st,
                                   std::string* err);
+// 14x14 / 7x7 maps: register-window stencil, one thread per channel pair (depthwise_cw.cu)
+cudaError_t launch_depthwise_cw(bf16* out, const bf16* in, const float* w9xC_scaled, const float* shift, int act, int n,
+                                int rows, int cols, int stride, int c, int pad_lo, cudaStream_t st);
 // generic SIMT 1x1 conv / FC: out[M][Cout] = in[M][K] * w[Cout][K]^T  (fp32 contexts, FC)
 cudaError_t launch_pointwise_simt(mnv1_dtype dt, void* out, const void* in, const float* w_f32,
                                   const bf16* w_bf16, long m, int k, int cout, Epilogue ep,

@@ -33,7 +33,8 @@ using namespace ptx;
 
 constexpr int SR_THREADS = 320;   // 4 gather + 4 epilogue + MMA/TMEM + producer warps
 constexpr int SR_C = 32;
-constexpr int SR_NI = 4;          // input ring depth (tiles in flight per CTA)
+constexpr int SR_NI = 8;          // input ring depth (tiles in flight per CTA)
+constexpr int SR_NA = 4;          // A tiles / accumulators in flight (two tiles share one 128B-swizzled 16 KB block)
 constexpr uint32_t SR_A_BYTES = 128 * 128;
 constexpr uint32_t SR_B_BYTES = 32 * 128;
 constexpr uint32_t SR_O_BYTES = 128 * 64;
@@ -80,9 +81,9 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
   const uint32_t sA = smem;                         // 2 x 16 KB
   const uint32_t sB = smem + 2 * SR_A_BYTES;        // 4 KB
   const uint32_t sO = sB + SR_B_BYTES;              // 2 x 8 KB
-  const uint32_t bars = sO + 2 * SR_O_BYTES;        // a_full[2] mma_done[2] tmem_free[2] in_full[NI] in_empty[NI]
-  const uint32_t a_full = bars, mma_done = bars + 16, tmem_free = bars + 32, in_full = bars + 48,
-                 in_empty = in_full + 8 * SR_NI;
+  const uint32_t bars = sO + 2 * SR_O_BYTES;        // a_full[NA] mma_done[NA] tmem_free[NA] in_full[NI] in_empty[NI]
+  const uint32_t a_full = bars, mma_done = a_full + 8 * SR_NA, tmem_free = mma_done + 8 * SR_NA,
+                 in_full = tmem_free + 8 * SR_NA, in_empty = in_full + 8 * SR_NI;
   const uint32_t tmem_slot = in_empty + 8 * SR_NI;
   const uint32_t sIn = bars + 256;                  // NI slots of slot_bytes
 
@@ -111,11 +112,11 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
   }
   if (tid == 0) {
     prefetch_tmap(&tmap_out);
-    for (int b = 0; b < 2; ++b) { mbar_init(a_full + 8 * b, 128); mbar_init(mma_done + 8 * b, 1); mbar_init(tmem_free + 8 * b, 4); }
+    for (int b = 0; b < SR_NA; ++b) { mbar_init(a_full + 8 * b, 128); mbar_init(mma_done + 8 * b, 1); mbar_init(tmem_free + 8 * b, 4); }
     for (int s = 0; s < SR_NI; ++s) { mbar_init(in_full + 8 * s, 1); mbar_init(in_empty + 8 * s, 4); }
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 64u);
+  if (warp == 8) tmem_alloc(tmem_slot, (uint32_t)(SR_NA * SR_C));
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -135,9 +136,13 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
     const bool pad_left = 2 * ox - p.pad_lo < 0, pad_right = 2 * ox - p.pad_lo + 2 >= p.cols;
     const uint32_t pad2 = p.pad_f16x2;
     const uint32_t bias2 = 0x64006400u, bias1 = 0x00006400u;
+    // row of the tile inside its image, stepped without a divide
+    const int oy_step = (int)(gridDim.x % (unsigned)Ho);
+    int oy = (int)(blockIdx.x % (unsigned)Ho);
+    const int sw = tid & 7;
     int i = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
-      const int slot = i % SR_NI, kin = i / SR_NI, buf = i & 1, k = i >> 1;
+      const int slot = i % SR_NI, kin = i / SR_NI, buf = i % SR_NA, k = i / SR_NA;
       mbar_wait(in_full + 8 * slot, (uint32_t)kin & 1u);
       uint32_t a[14];
       if (ox < Wo) {
@@ -156,7 +161,7 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
         a[12] = unbias(e8[0] | (e8[1] << 16) | bias2, bias2);
         a[13] = unbias(e8[2] | bias1, bias1);
         // padding: rows outside the image are tile-uniform, columns touch the first / last thread
-        const int oy = t % Ho, iy0 = 2 * oy - p.pad_lo;
+        const int iy0 = 2 * oy - p.pad_lo;
         const bool row_lo = iy0 < 0, row_hi = iy0 + 2 >= H;
         if (row_lo | row_hi | pad_left | pad_right) {
 #pragma unroll
@@ -179,14 +184,17 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
       // the slot's bytes are in registers: hand it back to the producer
       __syncwarp();
       if (lane == 0) mbar_arrive(in_empty + 8 * slot);
-      // A[buf] was last read by the MMAs of tile i-2
+      oy += oy_step;
+      if (oy >= Ho) oy -= Ho;
+      // A[buf] was last read by the MMAs of tile i-NA.  Tile `buf` is the 64-byte half (buf & 1) of
+      // the 128-byte rows of block buf >> 1: chunks 4h..4h+3 before the swizzle.
       if (k > 0) mbar_wait(mma_done + 8 * buf, (uint32_t)(k - 1) & 1u);
-      const uint32_t arow = sA + buf * SR_A_BYTES + tid * 128;
-      const int sw = tid & 7;
-      sts128(arow + ((0 ^ sw) << 4), a[0], a[1], a[2], a[3]);
-      sts128(arow + ((1 ^ sw) << 4), a[4], a[5], a[6], a[7]);
-      sts128(arow + ((2 ^ sw) << 4), a[8], a[9], a[10], a[11]);
-      sts128(arow + ((3 ^ sw) << 4), a[12], a[13], 0u, 0u);
+      const uint32_t arow = sA + (uint32_t)(buf >> 1) * SR_A_BYTES + tid * 128;
+      const int c0 = (buf & 1) * 4;
+      sts128(arow + (((c0 + 0) ^ sw) << 4), a[0], a[1], a[2], a[3]);
+      sts128(arow + (((c0 + 1) ^ sw) << 4), a[4], a[5], a[6], a[7]);
+      sts128(arow + (((c0 + 2) ^ sw) << 4), a[8], a[9], a[10], a[11]);
+      sts128(arow + (((c0 + 3) ^ sw) << 4), a[12], a[13], 0u, 0u);
       fence_proxy_async();
       mbar_arrive(a_full + 8 * buf);
     }
@@ -196,7 +204,7 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
     const bool leader = tid == 128;
     int i = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
-      const int buf = i & 1, k = i >> 1;
+      const int buf = i % SR_NA, k = i / SR_NA, sbuf = i & 1;
       mbar_wait(mma_done + 8 * buf, (uint32_t)k & 1u);
       tc_fence_after();
       uint32_t v[32];
@@ -205,10 +213,10 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_free + 8 * buf);
-      // staging buffer `buf` was read by the TMA store of tile i-2
+      // staging buffer `sbuf` was read by the TMA store of tile i-2
       if (leader) tma_store_wait_read<1>();
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      const uint32_t orow = sO + buf * SR_O_BYTES + row * 64;
+      const uint32_t orow = sO + sbuf * SR_O_BYTES + row * 64;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t o[4];
@@ -223,7 +231,7 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
       fence_proxy_async();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (leader) {
-        tma_store_2d(&tmap_out, sO + buf * SR_O_BYTES, 0, t * Wo);
+        tma_store_2d(&tmap_out, sO + sbuf * SR_O_BYTES, 0, t * Wo);
         tma_store_commit();
       }
     }
@@ -234,11 +242,12 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
       const uint64_t descB = umma_desc_sw128(sB);
       int i = 0;
       for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
-        const int buf = i & 1, k = i >> 1;
+        const int buf = i % SR_NA, k = i / SR_NA;
         if (k > 0) mbar_wait(tmem_free + 8 * buf, (uint32_t)(k - 1) & 1u);
         mbar_wait(a_full + 8 * buf, (uint32_t)k & 1u);
         tc_fence_after();
-        const uint64_t descA = umma_desc_sw128(sA + buf * SR_A_BYTES);
+        // K-slices of 32 bytes inside the 128-byte swizzle atom: tile half h starts at byte 64 h
+        const uint64_t descA = umma_desc_sw128(sA + (uint32_t)(buf >> 1) * SR_A_BYTES) + (uint64_t)((buf & 1) * 4);
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * SR_C);
         umma_f16(tmem_d, descA, descB, 0u);            // k = 0..15
         umma_f16(tmem_d, descA + 2, descB + 2, 1u);    // k = 16..31
@@ -264,7 +273,7 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64u);
+    tmem_dealloc(tmem_base, (uint32_t)(SR_NA * SR_C));
   }
 }
 

@@ -99,12 +99,12 @@ def _prep(ctx, mn, oracle_mod, x):
 
 @pytest.mark.parametrize("c,h,stride,pad", [(32, 112, 1, 0), (64, 112, 2, 0), (64, 112, 2, 1), (128, 56, 1, 1),
                                             (256, 28, 2, 1), (512, 14, 1, 0), (512, 14, 2, 1), (1024, 7, 1, 0),
-                                            (16, 10, 2, 0), (8, 9, 1, 0)])
+                                            (1024, 7, 1, 1), (16, 10, 2, 0), (8, 9, 1, 0)])
 def test_depthwise_layer(ctx, mn, oracle_mod, c, h, stride, pad):
     if h % stride:
         pytest.skip("odd size with stride 2")
     rng = np.random.default_rng(10 + c + h)
-    n = 2
+    n = 2 + pad          # 3 images in the TF-SAME cases: odd counts leave ragged last tiles / blocks
     x = _prep(ctx, mn, oracle_mod, (rng.random((n, c, h, h), dtype=np.float32) * 6))
     w = rng.standard_normal((c, 3, 3)).astype(np.float32) * 0.5
     sc = (0.5 + rng.random(c)).astype(np.float32)
@@ -119,6 +119,10 @@ def test_depthwise_layer(ctx, mn, oracle_mod, c, h, stride, pad):
     got = ctx.download_planar(out)
     ctx.set_pad_mode(mn.PAD_REF)
     assert rel_err(got, want) <= _tol(ctx, mn)
+    if ctx.dtype == mn.BF16 and (c, h, stride) == (1024, 7, 1):
+        assert ctx.last_kernel_name == "depthwise_cw_kernel"     # thread-per-channel-pair kernel, layer 26
+    if ctx.dtype == mn.BF16 and (c, h) == (512, 14):
+        assert ctx.last_kernel_name == "depthwise_ring_kernel"
 
 
 @pytest.mark.parametrize("cin,cout,h,n", [(32, 64, 112, 1), (64, 128, 56, 2), (128, 128, 56, 1), (128, 256, 28, 3),
