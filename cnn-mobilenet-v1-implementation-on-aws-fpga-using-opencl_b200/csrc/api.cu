@@ -466,6 +466,9 @@ static cudaError_t run_pointwise(mnv1_ctx* ctx, void* out, const void* in, const
   ctx->launches++;
   if (ctx->dtype == MNV1_BF16 && f->has_tmap && !force_simt) {
     ctx->err.clear();
+    cudaError_t ep = mnv1::launch_pointwise_pair((bf16*)out, (const bf16*)in, f, m, f->cin, f->cout, ctx->num_sms,
+                                                 ctx->stream, &ctx->err);
+    if (ep != cudaErrorNotSupported) { ctx->last_kernel = "pointwise_pair_kernel"; return ep; }
     ctx->last_kernel = "pointwise_tc_kernel";
     return mnv1::launch_pointwise_tc((bf16*)out, (const bf16*)in, f, m, f->cin, f->cout, ctx->num_sms,
                                      ctx->stream, &ctx->err);

@@ -135,6 +135,9 @@ cudaError_t launch_pointwise_simt(mnv1_dtype dt, void* out, const void* in, cons
 cudaError_t launch_pointwise_tc(bf16* out, const bf16* in, const mnv1_filter* f, long m, int k,
                                 int cout, int num_sms, cudaStream_t st, std::string* err);
 cudaError_t make_weight_tmap(mnv1_filter* f, std::string* err);
+// CTA-pair tcgen05 (cta_group::2) 1x1 conv for Cout % 256 == 0, K >= 256 (pointwise_pair.cu)
+cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* f, long m, int k, int cout, int num_sms,
+                                  cudaStream_t st, std::string* err);
 // fused depthwise -> pointwise block (bf16, fused_rb.cu); cudaErrorNotSupported = no variant, nothing launched
 cudaError_t launch_fused_dw_pw(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n,
                                int rows, int cols, int stride, int pad_lo, int num_sms, cudaStream_t st,

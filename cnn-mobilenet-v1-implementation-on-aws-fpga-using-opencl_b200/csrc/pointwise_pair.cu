@@ -1,20 +1,23 @@
-// pointwise_mc.cu — the 1x1 convolution for the tensor-bound layers (Cout a multiple of 256, K >= 256:
-// layers 13-27 of the MobileNet.c schedule) as a 2-CTA cluster kernel with a MULTICAST filter.
+// pointwise_pair.cu — the 1x1 convolution for the tensor-bound layers (Cout a multiple of 256, K >= 256:
+// layers 13-27 of the MobileNet.c schedule) on CTA PAIRS: tcgen05.mma.cta_group::2, one 256 x 256 tile per pair.
 //
-// Same contract and arithmetic as pointwise_tc.cu (`pointwise`, kernel.cl:94-114).  What the traces
-// of that kernel showed on the 512x512 layers (profiles/r01_pw_trace.txt): the UMMAs of a 128x256x512
-// tile need 4.1 k cycles, but the tile took 6-7.5 k because its 384 KB of operands (128 KB of A, 256 KB
-// of B) arrive at ~59 B/cycle per SM, and the epilogue with shared staging and bar.syncs another 4.1 k.
-// Here two CTAs of a cluster work on two m-tiles of the SAME n-tile: each loads its own A tile and HALF
-// of the filter tile and multicasts that half into both CTAs' shared memory, so a CTA asks L2 for 256 KB
-// per tile instead of 384 KB; the epilogue warps work independently (private staging, own TMA stores,
-// scale/shift batched before the TMEM wait) and need ~2.6 k cycles per tile.
+// Same contract and arithmetic as pointwise_tc.cu (`pointwise`, kernel.cl:94-114).  Why a second kernel:
+// on the 512x512 layers a 128x256x512 tile holds 4.1 k cycles of UMMA work but pointwise_tc needs 6-7.5 k,
+// and experiments/mma_fill.cu says why.  (1) With every SM pulling from L2, shared memory fills at no more
+// than ~84 B/cycle/SM, and only with >= 3 copies of 32 KB in flight; a 128x256 tile needs 48 KB per
+// 512-cycle k-block = 94 B/cycle, and the 3 x 48 KB ring that fits keeps 2 copies in flight (~65 B/cycle).
+// (2) One thread starts a TMA load every ~380 cycles, so two loads per k-block from one thread are
+// issue-bound at ~760 cycles.  A CTA pair fixes both: each CTA stages its own 128 rows of A and HALF of
+// the filter tile (the pair's UMMA reads the other half from the peer), 32 KB per k-block = 62 B/cycle
+// with a 4-deep ring, and each operand has its own issuing thread.
 //
-//   warp 0      TMA producer: A (128 x 64) + its half of B (128 x 64, multicast) per k-block; a slot is
-//               reused when BOTH CTAs' MMAs that read it have retired (empty barrier, 2 arrivals)
-//   warp 1      TMEM allocator + converged MMA issuer (one elected lane), tcgen05.commit multicast to the
-//               empty barriers of both CTAs
-//   warps 2-9   epilogue: two warps per TMEM lane quarter, alternate 64-column blocks
+//   warp 0      A producer: this CTA's 128 x 64 activation tile per k-block; the leader's thread also
+//               announces the k-block's bytes of BOTH CTAs on the leader's full barrier
+//   warp 10     filter producer: this CTA's half (128 output channels x 64) of the filter tile
+//   warp 1      TMEM allocator; in the leader CTA the converged MMA issuer (one elected lane,
+//               UMMA 256 x 256 x 16), tcgen05.commit multicast to the barriers of both CTAs
+//   warps 2-9   epilogue: two warps per TMEM lane quarter, alternate 64-column blocks, private
+//               staging, own TMA stores
 #include <cstdio>
 #include <cstdlib>
 
@@ -28,7 +31,8 @@ using namespace ptx;
 
 constexpr int MC_BK = 64;
 constexpr int MC_EPI_WARPS = 8;
-constexpr int MC_THREADS = 64 + 32 * MC_EPI_WARPS;
+constexpr int MC_THREADS = 64 + 32 * MC_EPI_WARPS + 32;
+constexpr int MC_W_BPROD = 2 + MC_EPI_WARPS;
 constexpr int MC_MAX_STAGES = 8;
 constexpr uint32_t MC_A_BYTES = 128 * 128;        // 128 rows x 64 bf16
 constexpr uint32_t MC_BH_BYTES = 128 * 128;       // half of the filter tile: 128 output channels x 64 bf16
@@ -47,6 +51,8 @@ struct McParams {
   long M;
   int K, Cout, stages;
   unsigned long long* trace;
+  bf16* out;
+  int dbg;      // MNV1_PP_DBG (timing experiments only): 1 = st.global from registers instead of staging + TMA store, 2 = no operand loads, 4 = no epilogue output
 };
 
 template <bool RELU>
@@ -90,19 +96,17 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (lane == 0 && !(p.dbg & 2)) {
       const uint32_t full_leader = mapa_shared(full, 0);
       int stage = 0; uint32_t phase = 0;
       for (long u = cid; u < num_units; u += num_clusters) {
         const int m_idx = (int)((u / n_tiles) * 2 + rank) * 128;
-        const int n_idx = (int)(u % n_tiles) * 256 + (int)rank * 128;     // the half of the filter tile this CTA holds
         for (int kb = 0; kb < num_kb; ++kb) {
           if (kb == 0) pp_stamp(p.trace, 0, u / num_clusters, 0);
           mbar_wait(empty + 8u * stage, phase ^ 1u);       // the pair's MMAs that read this slot have retired
           const uint32_t sa = sRing + (uint32_t)stage * MC_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(full + 8u * stage, 2 * MC_STAGE_BYTES);   // both CTAs' bytes complete on the leader's barrier
           tma_load_2d_pair(sa, &tmap_a, full_leader + 8u * stage, kb * MC_BK, m_idx);
-          tma_load_2d_pair(sa + MC_A_BYTES, &tmap_b, full_leader + 8u * stage, kb * MC_BK, n_idx);
           if (kb == num_kb - 1) pp_stamp(p.trace, 0, u / num_clusters, 2);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
@@ -121,7 +125,7 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (elected) pp_stamp(p.trace, 1, u / num_clusters, 1);
       const uint32_t tmem_d = tmem_base + (uint32_t)as * MC_ACC_COLS;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full + 8u * stage, phase);
+        if (!(p.dbg & 2)) mbar_wait(full + 8u * stage, phase);
         tc_fence_after();
         if (kb == 0 && elected) pp_stamp(p.trace, 1, u / num_clusters, 2);
         const uint32_t sa = sRing + (uint32_t)stage * MC_STAGE_BYTES;
@@ -134,6 +138,22 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       umma_commit_pair_if(elected, tm_full + 8u * as);                     // both CTAs' accumulators are complete
       if (elected) pp_stamp(p.trace, 1, u / num_clusters, 3);
       if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+  } else if (warp == MC_W_BPROD) {
+    // ================= filter producer =================
+    // Its bytes are counted by the leader's expect_tx (a complete_tx that lands first only makes the
+    // count negative for a while: the phase cannot complete before that arrival).
+    if (lane == 0 && !(p.dbg & 2)) {
+      const uint32_t full_leader = mapa_shared(full, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (long u = cid; u < num_units; u += num_clusters) {
+        const int n_idx = (int)(u % n_tiles) * 256 + (int)rank * 128;     // the half of the filter tile this CTA holds
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty + 8u * stage, phase ^ 1u);
+          tma_load_2d_pair(sRing + (uint32_t)stage * MC_STAGE_BYTES + MC_A_BYTES, &tmap_b, full_leader + 8u * stage, kb * MC_BK, n_idx);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
     }
   } else {
     // ================= epilogue warps 2..9: independent, private staging =================
@@ -185,10 +205,21 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             q[2 * j + 1] = pack2<RELU>(fmaf(__uint_as_float(v[4 * j + 2]), s4[j].z, t4[j].z), fmaf(__uint_as_float(v[4 * j + 3]), s4[j].w, t4[j].w), p.cap2);
           }
           if (half == 0) tmem_ld32_nowait(taddr + (uint32_t)(b * 64 + 32), v);   // second half under the stores
+          if (p.dbg & 4) {
+          } else if (p.dbg & 1) {
+            const long row = (long)m_idx + lane;
+            if (row < p.M) {
+              uint4* gp = reinterpret_cast<uint4*>(p.out + row * p.Cout + n_idx + b * 64 + half * 32);
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) gp[c4] = make_uint4(q[4 * c4], q[4 * c4 + 1], q[4 * c4 + 2], q[4 * c4 + 3]);
+            }
+          } else {
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4)
             sts128(sbuf + row_off + (((uint32_t)(4 * half + c4) ^ row_x) << 4), q[4 * c4], q[4 * c4 + 1], q[4 * c4 + 2], q[4 * c4 + 3]);
+          }
         }
+        if (p.dbg & 5) continue;
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {   // box = 64 columns x 32 rows; rows past M are clipped by the TMA unit
@@ -257,6 +288,8 @@ cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* 
   p.scale = f->scale; p.shift = f->shift;
   p.cap2 = f->act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
   p.M = m; p.K = k; p.Cout = cout; p.stages = stages;
+  p.out = out;
+  { static const char* de = getenv("MNV1_PP_DBG"); p.dbg = de ? atoi(de) : 0; }
   static unsigned long long* d_trace_buf = nullptr;
   const char* trace_path = getenv("MNV1_PW_TRACE");
   if (trace_path) {

@@ -68,7 +68,7 @@ def test_kat_pointwise_three_way(ctx, mn, oracle_mod, cin, cout, h, hi):
     ctx.pointwise(out, xin, f, h, h, cin, cout)
     got = ctx.download_planar(out)
     if ctx.dtype == mn.BF16 and cout % 64 == 0 and cin % 8 == 0:
-        assert ctx.last_kernel_name in ("pointwise_tc_kernel", "pointwise_mc_kernel")   # tcgen05 path, never the SIMT GEMM
+        assert ctx.last_kernel_name in ("pointwise_tc_kernel", "pointwise_pair_kernel")   # tcgen05 path, never the SIMT GEMM
     assert np.array_equal(got, want)
 
 
@@ -144,7 +144,7 @@ def test_pointwise_layer(ctx, mn, oracle_mod, cin, cout, h, n):
     got = ctx.download_planar(out)
     assert rel_err(got, want) <= _tol(ctx, mn)
     if ctx.dtype == mn.BF16 and cout % 64 == 0 and cin % 8 == 0:
-        assert ctx.last_kernel_name in ("pointwise_tc_kernel", "pointwise_mc_kernel")   # tcgen05 path, never the SIMT GEMM
+        assert ctx.last_kernel_name in ("pointwise_tc_kernel", "pointwise_pair_kernel")   # tcgen05 path, never the SIMT GEMM
         # the CUDA-core GEMM must agree with the tensor-core one to the same tolerance
         out2 = ctx.malloc(n, cout, h, h)
         ctx.pointwise(out2, xin, f, h, h, cin, cout, simt=True)
