@@ -267,7 +267,7 @@ class Context:
                                     C.c_void_p(prob_ptr)))
 
     def forward_submit(self, images_ptr: int, n: int, logits_ptr: int, top1_ptr: int, prob_ptr: int) -> int:
-        """Pipelined mnv1_forward: returns a ticket; up to two batches in flight."""
+        """Pipelined mnv1_forward: returns a ticket; up to three batches in flight."""
         t = C.c_long(-1)
         self._ck(lib().mnv1_forward_submit(self.h, C.c_void_p(images_ptr), n, C.c_void_p(logits_ptr or None),
                                            C.c_void_p(top1_ptr or None), C.c_void_p(prob_ptr or None), C.byref(t)))

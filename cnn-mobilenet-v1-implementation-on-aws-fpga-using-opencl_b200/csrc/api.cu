@@ -89,15 +89,18 @@ struct mnv1_ctx {
   float* h_logits = nullptr;
   int* h_top1 = nullptr;
   float* h_prob = nullptr;
-  // two in-flight batches for mnv1_forward_submit / _wait: while batch i computes, batch i+1's
-  // images are copied in (copy stream) and batch i-1's results are copied out (d2h stream)
+  // kSlots in-flight batches for mnv1_forward_submit / _wait: while batch i computes, the images of
+  // batches i+1 and i+2 are copied in (copy stream) and batch i-1's results are copied out (d2h
+  // stream).  Three, not two: the upload of a 256-image batch (38.5 MB over PCIe, ~0.77 ms) is
+  // almost as long as its kernels (0.86 ms), so with two slots any host wake-up delay stalls the GPU.
+  static constexpr int kSlots = 3;
   struct Slot {
     uint8_t* d_images = nullptr; float* d_logits = nullptr; int* d_top1 = nullptr; float* d_prob = nullptr;
     uint8_t* h_images = nullptr; float* h_logits = nullptr; int* h_top1 = nullptr; float* h_prob = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_compute = nullptr, ev_done = nullptr;
     bool busy = false; int n = 0; long ticket = -1;
     float* u_logits = nullptr; int* u_top1 = nullptr; float* u_prob = nullptr;  // unpinned user outputs
-  } slots[2];
+  } slots[kSlots];
   cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
   long next_ticket = 0;
   long graph_kernels = 30;
@@ -904,8 +907,8 @@ int mnv1_forward_submit(mnv1_ctx* ctx, const uint8_t* images, int n, float* logi
   int rc = check_ready(ctx, n);
   if (rc) return rc;
   if (!images || !ticket) return fail(ctx, MNV1_EINVAL, "forward_submit: images / ticket is null");
-  mnv1_ctx::Slot& sl = ctx->slots[ctx->next_ticket & 1];
-  if ((rc = finish_slot(ctx, sl)) != MNV1_OK) return rc;  // the batch submitted two calls ago
+  mnv1_ctx::Slot& sl = ctx->slots[ctx->next_ticket % mnv1_ctx::kSlots];
+  if ((rc = finish_slot(ctx, sl)) != MNV1_OK) return rc;  // the batch submitted kSlots calls ago
   sl.n = n; sl.ticket = ctx->next_ticket;
   // images: straight from the caller's buffer when it is page-locked, else through the slot's staging copy
   const uint8_t* src = images;
@@ -941,7 +944,8 @@ int mnv1_forward_submit(mnv1_ctx* ctx, const uint8_t* images, int n, float* logi
 
 int mnv1_forward_wait(mnv1_ctx* ctx, long ticket) {
   if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
-  mnv1_ctx::Slot& sl = ctx->slots[ticket & 1];
+  if (ticket < 0 || !ctx) return fail(ctx, MNV1_EINVAL, "forward_wait: unknown ticket");
+  mnv1_ctx::Slot& sl = ctx->slots[ticket % mnv1_ctx::kSlots];
   if (ticket < 0 || ticket >= ctx->next_ticket) return fail(ctx, MNV1_EINVAL, "forward_wait: unknown ticket");
   if (sl.ticket != ticket) return MNV1_OK;  // already retired by a later submit
   return finish_slot(ctx, sl);

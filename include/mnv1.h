@@ -147,7 +147,7 @@ int mnv1_forward(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int
                  float* top1_prob);
 /* the same, split so that consecutive batches overlap: submit enqueues H2D (copy stream), the
  * graph (context stream) and D2H (third stream) and returns; wait blocks until that batch's
- * outputs are in the caller's arrays.  Two batches may be in flight; submitting a third first
+ * outputs are in the caller's arrays.  Three batches may be in flight; submitting a fourth first
  * retires the oldest.  Page-locked caller buffers (mnv1_host_alloc) are copied from / to directly. */
 int mnv1_forward_submit(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int* top1,
                         float* top1_prob, long* ticket);

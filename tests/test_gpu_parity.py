@@ -362,17 +362,19 @@ def test_errors_and_empty(mn):
     c.close()
 
 
-def test_pipelined_forward_matches_blocking(mn, synth_net):
-    """mnv1_forward_submit/_wait with two batches in flight returns the same bits as mnv1_forward,
-    for pinned (torch) and pageable (numpy) caller buffers."""
+@pytest.mark.parametrize("depth", [2, 3, 5])
+def test_pipelined_forward_matches_blocking(mn, synth_net, depth):
+    """mnv1_forward_submit/_wait with `depth` batches outstanding (the library keeps three in flight;
+    submitting more retires the oldest) returns the same bits as mnv1_forward, for pinned (torch) and
+    pageable (numpy) caller buffers."""
     import torch
     from mnv1_b200 import synth
     c = _net_ctx(mn, mn.BF16, synth_net)
     n = 32
-    batches = [synth.images(n, first=k * n) for k in range(4)]
+    batches = [synth.images(n, first=k * n) for k in range(7)]
     want = [c.forward(b) for b in batches]
     outs = []
-    prev = None
+    pending = []
     for k, b in enumerate(batches):
         pinned = k % 2 == 0
         if pinned:
@@ -386,11 +388,11 @@ def test_pipelined_forward_matches_blocking(mn, synth_net):
             p1 = np.empty(n, np.float32)
             ptrs = (hi.ctypes.data, lg.ctypes.data, t1.ctypes.data, p1.ctypes.data)
             outs.append((hi, lg, t1, p1))
-        t = c.forward_submit(ptrs[0], n, ptrs[1], ptrs[2], ptrs[3])
-        if prev is not None:
-            c.forward_wait(prev)
-        prev = t
-    c.forward_wait(prev)
+        pending.append(c.forward_submit(ptrs[0], n, ptrs[1], ptrs[2], ptrs[3]))
+        if len(pending) == depth:
+            c.forward_wait(pending.pop(0))
+    for t in pending:
+        c.forward_wait(t)
     for (hi, lg, t1, p1), (wl, wt, wp) in zip(outs, want):
         lg = lg.numpy() if hasattr(lg, "numpy") and not isinstance(lg, np.ndarray) else lg
         t1 = t1.numpy() if not isinstance(t1, np.ndarray) else t1
