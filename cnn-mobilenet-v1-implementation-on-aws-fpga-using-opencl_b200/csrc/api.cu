@@ -429,7 +429,8 @@ static cudaError_t run_stem(mnv1_ctx* ctx, void* out, const uint8_t* r, const ui
   ctx->launches++;
   if (ctx->dtype == MNV1_BF16 && f->prepared && f->prep_scale == ctx->in_scale && f->prep_bias == ctx->in_bias) {
     ctx->err.clear();
-    if (!getenv("MNV1_NO_STEM_ROWS")) {
+    static const bool no_rows = getenv("MNV1_NO_STEM_ROWS") != nullptr;   // debug switch, read once
+    if (!no_rows) {
       cudaError_t er = mnv1::launch_stem_rows((bf16*)out, a, f->wq, f->h_scale.empty() ? nullptr : f->h_scale.data(),
                                               f->h_shift2, f->p0, (int)f->act, ctx->num_sms, ctx->stream, &ctx->err);
       if (er != cudaErrorNotSupported) { ctx->last_kernel = "stem_rows_kernel"; return er; }
@@ -446,7 +447,8 @@ static cudaError_t run_depthwise(mnv1_ctx* ctx, void* out, const void* in, const
   ctx->launches++;
   if (ctx->dtype == MNV1_BF16 && f->w_scaled) {
     ctx->err.clear();
-    if (!getenv("MNV1_NO_CW")) {
+    static const bool no_cw = getenv("MNV1_NO_CW") != nullptr;            // debug switch, read once
+    if (!no_cw) {
       cudaError_t ec = mnv1::launch_depthwise_cw((bf16*)out, (const bf16*)in, f->w_scaled, f->shift, (int)f->act, n, rows,
                                                  cols, stride, f->cout, pad_lo_for(ctx, stride), ctx->stream);
       if (ec != cudaErrorNotSupported) { ctx->last_kernel = "depthwise_cw_kernel"; return ec; }
