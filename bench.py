@@ -163,8 +163,8 @@ def run_ours(args):
         logits = torch.empty(batch, 1000, dtype=torch.float32, device=dev)
         top1 = torch.empty(batch, dtype=torch.int32, device=dev)
         prob = torch.empty(batch, dtype=torch.float32, device=dev)
-        # N > 1: the logits all-gather of step i runs on its own stream under the kernels of step i+1
-        # (two logits / gather buffers); it stays inside the timed region, one collective per step
+        # N > 1: one logits all-gather per step inside the timed region (see GATHER_INLINE); two logits /
+        # gather buffers so that the overlapped variant can run under the kernels of step i+1
         logits2 = [logits, torch.empty_like(logits)] if world > 1 else [logits]
         gathered = [torch.empty(world * batch, 1000, dtype=torch.float32, device=dev) for _ in range(2)] if world > 1 else None
         comm = torch.cuda.Stream(device=dev) if world > 1 else None
@@ -177,7 +177,11 @@ def run_ours(args):
                 stream.wait_event(ev_comm[k])     # the gather that last read logits2[k] is done
             ctx.forward_device(imgs[i % N_ROTATE].data_ptr(), batch, logits2[k].data_ptr(), top1.data_ptr(),
                                prob.data_ptr())
-            if world > 1:
+            if world > 1 and GATHER_INLINE:
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(gathered[k], logits2[k])
+                    ev_comm[k].record(stream)
+            elif world > 1:
                 ev_fwd[k].record(stream)
                 with torch.cuda.stream(comm):
                     comm.wait_event(ev_fwd[k])
@@ -395,6 +399,14 @@ def run_reference(args):
            "cpu_baseline": res,
            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out, default=float))
+
+
+# N > 1: where the per-step logits all-gather runs.  "inline" (default) = on the compute stream after the
+# step's last kernel; "overlap" = on its own stream under the next step's kernels.  Overlapping loses: the
+# forward kernels are persistent, one CTA per SM, so every SM the NCCL kernel holds delays one CTA of the
+# kernel running beside it by the gather's whole duration (8 GPUs: 0.936 ms per step inline, 0.957 overlapped;
+# 2 GPUs: 0.890 / 0.895).
+GATHER_INLINE = os.environ.get("MNV1_GATHER", "inline") == "inline"
 
 
 def main():
