@@ -291,7 +291,7 @@ def run_ours(args):
             if os.path.exists(tpath):
                 traffic = json.load(open(tpath)).get(dom)
             ach = d["bytes"] / (d["us"] * 1e-6) / 1e9
-            roof = {"kernel": {"dw": "depthwise_tma_kernel", "pw": "pointwise_tc_kernel", "stem": "stem_rows_kernel",
+            roof = {"kernel": {"dw": "depthwise_ring_kernel", "pw": "pointwise_pair_kernel", "stem": "stem_rows_kernel",
                                "dw+pw": "fused_rb_kernel", "pool": "pool_kernel", "fc": "head"}[dom],
                     "bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": round(ach / peaks["hbm_gbs"], 3), "traffic": traffic,
