@@ -21,10 +21,50 @@ int read_ppm(const char* path, uint8_t* out, int height, int width, std::string*
 
 static thread_local std::string g_last_error;
 
-bool mnv1::pdl_enabled() {
-  static const bool on = getenv("MNV1_NO_PDL") == nullptr;
-  return on;
+const mnv1::Switches& mnv1::switches() {
+  static Switches sw;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    sw.no_pdl = getenv("MNV1_NO_PDL") != nullptr;
+    sw.no_pair = getenv("MNV1_NO_PAIR") != nullptr;
+    sw.no_cw = getenv("MNV1_NO_CW") != nullptr;
+    sw.no_stem_rows = getenv("MNV1_NO_STEM_ROWS") != nullptr;
+    sw.no_fused_head = getenv("MNV1_NO_FUSED_HEAD") != nullptr;
+    sw.no_fused_pair = getenv("MNV1_NO_FUSED_PAIR") != nullptr;
+    sw.rb_mask = getenv("MNV1_RB_MASK") ? strtol(getenv("MNV1_RB_MASK"), nullptr, 0) : ~0L;
+  });
+  return sw;
 }
+bool mnv1::pdl_enabled() { return !switches().no_pdl; }
+
+cudaError_t mnv1::ensure_dyn_smem(const void* fn, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;   // (function, device) -> bytes granted
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = done.find({fn, dev});
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[{fn, dev}] = bytes;
+  return e;
+}
+
+// Every entry point that takes a context runs on the context's device, whatever device the calling
+// thread had current, and leaves the thread's current device as it found it.
+struct DeviceGuard {
+  int prev = -1, dev;
+  explicit DeviceGuard(int d) : dev(d) {
+    if (dev < 0) return;                                   // null context: the callee reports it
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (dev >= 0 && prev >= 0 && prev != dev) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define GUARD(ctx) DeviceGuard guard_((ctx) ? (ctx)->device : -1)
 
 struct LayerDef { int kind, cin, cout, hin, hout, stride; long w_off, w_cnt, c_off; };
 
@@ -107,7 +147,21 @@ struct mnv1_ctx {
   std::map<GraphKey, cudaGraphExec_t> graphs;
   bool use_graph = true;
   bool use_fused = true;   // depthwise->pointwise block fusion inside mnv1_forward*
+  // staging for the planar <-> NHWC boundary copies and mnv1_softmax: grown on demand, then reused, so the
+  // per-layer loop of the host programs allocates nothing after its first pass
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
 };
+
+static void* scratch(mnv1_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return ctx->scratch;
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_bytes = 0;
+  const size_t want = (bytes + (size_t(1) << 20) - 1) & ~((size_t(1) << 20) - 1);
+  if (cudaMalloc(&ctx->scratch, want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  ctx->scratch_bytes = want;
+  return ctx->scratch;
+}
 
 static int fail(mnv1_ctx* ctx, int code, const std::string& msg) {
   g_last_error = msg;
@@ -155,7 +209,8 @@ int mnv1_ctx_create(int device, mnv1_dtype dtype, mnv1_ctx** out) {
     return fail(nullptr, MNV1_ECUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
                                          " (this library has no CPU fallback)");
   if (device < 0 || device >= count) return fail(nullptr, MNV1_EINVAL, "device index out of range");
-  CK(nullptr, cudaSetDevice(device));
+  (void)mnv1::switches();          // environment switches are read here, once per process
+  DeviceGuard guard_(device);
   cudaDeviceProp prop;
   CK(nullptr, cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
@@ -196,9 +251,12 @@ int mnv1_filter_destroy(mnv1_ctx* ctx, mnv1_filter* f);
 
 int mnv1_ctx_destroy(mnv1_ctx* ctx) {
   if (!ctx) return MNV1_OK;
-  cudaSetDevice(ctx->device);
+  GUARD(ctx);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
   free_plan(ctx);
+  cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_bytes = 0;
   for (auto& f : ctx->net) { if (f) mnv1_filter_destroy(ctx, f); f = nullptr; }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -210,6 +268,7 @@ int mnv1_ctx_destroy(mnv1_ctx* ctx) {
 }
 
 int mnv1_ctx_set_stream(mnv1_ctx* ctx, void* s) {
+  GUARD(ctx);
   if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
   if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   ctx->stream = (cudaStream_t)s;
@@ -219,6 +278,7 @@ int mnv1_ctx_set_stream(mnv1_ctx* ctx, void* s) {
   return MNV1_OK;
 }
 int mnv1_ctx_set_pad_mode(mnv1_ctx* ctx, mnv1_pad pad) {
+  GUARD(ctx);
   if (!ctx || (pad != MNV1_PAD_REF && pad != MNV1_PAD_TFSAME)) return fail(ctx, MNV1_EINVAL, "bad pad mode");
   ctx->pad = pad;
   for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
@@ -226,6 +286,7 @@ int mnv1_ctx_set_pad_mode(mnv1_ctx* ctx, mnv1_pad pad) {
   return MNV1_OK;
 }
 int mnv1_ctx_set_input_transform(mnv1_ctx* ctx, float scale, float bias) {
+  GUARD(ctx);
   if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
   ctx->in_scale = scale; ctx->in_bias = bias;
   for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
@@ -233,16 +294,19 @@ int mnv1_ctx_set_input_transform(mnv1_ctx* ctx, float scale, float bias) {
   return MNV1_OK;
 }
 int mnv1_ctx_enable_timing(mnv1_ctx* ctx, int on) {
+  GUARD(ctx);
   if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
   ctx->timing = on != 0;
   return MNV1_OK;
 }
 int mnv1_sync(mnv1_ctx* ctx) {
+  GUARD(ctx);
   if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   return MNV1_OK;
 }
 int mnv1_last_kernel_ms(mnv1_ctx* ctx, float* ms) {
+  GUARD(ctx);
   if (!ctx || !ms) return fail(ctx, MNV1_EINVAL, "null arg");
   if (!ctx->timing || !ctx->ev_valid) return fail(ctx, MNV1_ESTATE, "no timed launch yet");
   CK(ctx, cudaEventSynchronize(ctx->ev1));
@@ -254,6 +318,7 @@ const char* mnv1_last_kernel_name(const mnv1_ctx* ctx) { return ctx ? ctx->last_
 
 // ---------------------------------------------------------------- buffers
 int mnv1_malloc(mnv1_ctx* ctx, int n, int c, int h, int w, mnv1_buf** out) {
+  GUARD(ctx);
   if (!ctx || !out || n < 0 || c <= 0 || h <= 0 || w <= 0) return fail(ctx, MNV1_EINVAL, "bad malloc shape");
   std::unique_ptr<mnv1_buf> b(new mnv1_buf);
   b->n = n; b->c = c; b->h = h; b->w = w;
@@ -266,6 +331,7 @@ int mnv1_malloc(mnv1_ctx* ctx, int n, int c, int h, int w, mnv1_buf** out) {
   return MNV1_OK;
 }
 int mnv1_malloc_u8(mnv1_ctx* ctx, size_t bytes, mnv1_buf** out) {
+  GUARD(ctx);
   if (!ctx || !out) return fail(ctx, MNV1_EINVAL, "null arg");
   std::unique_ptr<mnv1_buf> b(new mnv1_buf);
   b->bytes = bytes; b->is_u8 = true;
@@ -277,6 +343,7 @@ int mnv1_malloc_u8(mnv1_ctx* ctx, size_t bytes, mnv1_buf** out) {
   return MNV1_OK;
 }
 int mnv1_free(mnv1_ctx* ctx, mnv1_buf* b) {
+  GUARD(ctx);
   if (!b) return MNV1_OK;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   if (b->owned && b->d) cudaFree(b->d);
@@ -286,37 +353,36 @@ int mnv1_free(mnv1_ctx* ctx, mnv1_buf* b) {
 void* mnv1_buf_device_ptr(mnv1_buf* b) { return b ? b->d : nullptr; }
 
 int mnv1_upload_u8(mnv1_ctx* ctx, mnv1_buf* b, const uint8_t* host, size_t bytes) {
+  GUARD(ctx);
   if (!ctx || !b || !b->is_u8 || bytes > b->bytes || (!host && bytes)) return fail(ctx, MNV1_EINVAL, "bad upload_u8");
   if (bytes) CK(ctx, cudaMemcpyAsync(b->d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CK(ctx, cudaStreamSynchronize(ctx->stream));  // CL_TRUE blocking write, MobileNet.c:350
   return MNV1_OK;
 }
 int mnv1_upload_planar(mnv1_ctx* ctx, mnv1_buf* b, const float* host) {
+  GUARD(ctx);
   if (!ctx || !b || b->is_u8 || (!host && b->bytes)) return fail(ctx, MNV1_EINVAL, "bad upload_planar");
   if (!b->bytes) return MNV1_OK;
   const size_t elems = (size_t)b->n * b->c * b->h * b->w;
-  float* stage = nullptr;
-  cudaError_t e = cudaMalloc(&stage, elems * 4);
-  if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "staging cudaMalloc failed");
-  e = cudaMemcpyAsync(stage, host, elems * 4, cudaMemcpyHostToDevice, ctx->stream);
+  float* stage = (float*)scratch(ctx, elems * 4);
+  if (!stage) return fail(ctx, MNV1_ENOMEM, "staging cudaMalloc failed");
+  cudaError_t e = cudaMemcpyAsync(stage, host, elems * 4, cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) e = mnv1::launch_nchw_to_nhwc(ctx->dtype, b->d, stage, b->n, b->c, b->h, b->w, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(stage);
   ctx->launches++;
   if (e != cudaSuccess) return fail_cuda(ctx, e, "upload_planar");
   return MNV1_OK;
 }
 int mnv1_download_planar(mnv1_ctx* ctx, mnv1_buf* b, float* host) {
+  GUARD(ctx);
   if (!ctx || !b || b->is_u8 || (!host && b->bytes)) return fail(ctx, MNV1_EINVAL, "bad download_planar");
   if (!b->bytes) return MNV1_OK;
   const size_t elems = (size_t)b->n * b->c * b->h * b->w;
-  float* stage = nullptr;
-  cudaError_t e = cudaMalloc(&stage, elems * 4);
-  if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "staging cudaMalloc failed");
-  e = mnv1::launch_nhwc_to_nchw(ctx->dtype, stage, b->d, b->n, b->c, b->h, b->w, ctx->stream);
+  float* stage = (float*)scratch(ctx, elems * 4);
+  if (!stage) return fail(ctx, MNV1_ENOMEM, "staging cudaMalloc failed");
+  cudaError_t e = mnv1::launch_nhwc_to_nchw(ctx->dtype, stage, b->d, b->n, b->c, b->h, b->w, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(host, stage, elems * 4, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(stage);
   ctx->launches++;
   if (e != cudaSuccess) return fail_cuda(ctx, e, "download_planar");
   return MNV1_OK;
@@ -338,6 +404,7 @@ static uint16_t f32_to_bf16_rne(float x) {
 
 int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, int cout, const float* scale,
                        const float* shift, mnv1_act act, mnv1_filter** out) {
+  GUARD(ctx);
   if (!ctx || !w || !out || cin <= 0 || cout <= 0) return fail(ctx, MNV1_EINVAL, "bad filter_create args");
   std::unique_ptr<mnv1_filter> f(new mnv1_filter);
   f->kind = kind; f->cin = cin; f->cout = cout; f->act = act;
@@ -400,6 +467,7 @@ int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, i
   return MNV1_OK;
 }
 int mnv1_filter_destroy(mnv1_ctx* ctx, mnv1_filter* f) {
+  GUARD(ctx);
   if (!f) return MNV1_OK;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   cudaFree(f->w_f32); cudaFree(f->w_scaled); cudaFree(f->w_bf16); cudaFree(f->wq); cudaFree(f->shift2); cudaFree(f->scale); cudaFree(f->shift);
@@ -429,8 +497,7 @@ static cudaError_t run_stem(mnv1_ctx* ctx, void* out, const uint8_t* r, const ui
   ctx->launches++;
   if (ctx->dtype == MNV1_BF16 && f->prepared && f->prep_scale == ctx->in_scale && f->prep_bias == ctx->in_bias) {
     ctx->err.clear();
-    static const bool no_rows = getenv("MNV1_NO_STEM_ROWS") != nullptr;   // debug switch, read once
-    if (!no_rows) {
+    if (!mnv1::switches().no_stem_rows) {
       cudaError_t er = mnv1::launch_stem_rows((bf16*)out, a, f->wq, f->h_scale.empty() ? nullptr : f->h_scale.data(),
                                               f->h_shift2, f->p0, (int)f->act, ctx->num_sms, ctx->stream, &ctx->err);
       if (er != cudaErrorNotSupported) { ctx->last_kernel = "stem_rows_kernel"; return er; }
@@ -447,8 +514,7 @@ static cudaError_t run_depthwise(mnv1_ctx* ctx, void* out, const void* in, const
   ctx->launches++;
   if (ctx->dtype == MNV1_BF16 && f->w_scaled) {
     ctx->err.clear();
-    static const bool no_cw = getenv("MNV1_NO_CW") != nullptr;            // debug switch, read once
-    if (!no_cw) {
+    if (!mnv1::switches().no_cw) {
       cudaError_t ec = mnv1::launch_depthwise_cw((bf16*)out, (const bf16*)in, f->w_scaled, f->shift, (int)f->act, n, rows,
                                                  cols, stride, f->cout, pad_lo_for(ctx, stride), ctx->stream);
       if (ec != cudaErrorNotSupported) { ctx->last_kernel = "depthwise_cw_kernel"; return ec; }
@@ -512,6 +578,7 @@ static int convolute_common(mnv1_ctx* ctx, mnv1_buf* out, const uint8_t* r, cons
 
 int mnv1_convolute(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in_r, const mnv1_buf* in_g, const mnv1_buf* in_b,
                    const mnv1_filter* f, int rows, int cols, int filtersize, int stride, int op_size) {
+  GUARD(ctx);
   if (!in_r || !in_g || !in_b || !in_r->is_u8 || !in_g->is_u8 || !in_b->is_u8)
     return fail(ctx, MNV1_EINVAL, "convolute: r/g/b must be u8 buffers");
   size_t avail = in_r->bytes < in_g->bytes ? in_r->bytes : in_g->bytes;
@@ -521,6 +588,7 @@ int mnv1_convolute(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in_r, const mnv
 }
 int mnv1_convolute_rgb(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in_rgb, const mnv1_filter* f, int rows,
                        int cols, int filtersize, int stride, int op_size) {
+  GUARD(ctx);
   if (!in_rgb || !in_rgb->is_u8) return fail(ctx, MNV1_EINVAL, "convolute_rgb: image must be a u8 buffer");
   const uint8_t* p = (const uint8_t*)in_rgb->d;
   return convolute_common(ctx, out, p, p + 1, p + 2, 3, in_rgb->bytes, f, rows, cols, filtersize, stride, op_size);
@@ -528,6 +596,7 @@ int mnv1_convolute_rgb(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in_rgb, con
 
 int mnv1_depthwise(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* f, int rows, int cols,
                    int filtersize, int stride, int op_size) {
+  GUARD(ctx);
   if (!ctx || !out || !in || !f) return fail(ctx, MNV1_EINVAL, "depthwise: null argument");
   if (f->kind != MNV1_DEPTHWISE || f->cout != op_size) return fail(ctx, MNV1_EINVAL, "depthwise: filter mismatch");
   if (filtersize != 3) return fail(ctx, MNV1_EUNSUPPORTED, "depthwise: only 3x3 (K = 3, MobileNet.c:15)");
@@ -561,16 +630,19 @@ static int pointwise_impl(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, cons
 }
 int mnv1_pointwise(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* f, int rows, int cols,
                    int filtersize, int op_size) {
+  GUARD(ctx);
   return pointwise_impl(ctx, out, in, f, rows, cols, filtersize, op_size, false);
 }
 // the CUDA-core GEMM on any context (what fp32 contexts always run); used to cross-check the
 // tcgen05 kernel on the device
 int mnv1_pointwise_simt(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* f, int rows, int cols,
                         int filtersize, int op_size) {
+  GUARD(ctx);
   return pointwise_impl(ctx, out, in, f, rows, cols, filtersize, op_size, true);
 }
 
 int mnv1_pool(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, int rows, int cols, int filtersize, int op_size) {
+  GUARD(ctx);
   if (!ctx || !out || !in) return fail(ctx, MNV1_EINVAL, "pool: null argument");
   if (rows != filtersize || cols != filtersize)
     return fail(ctx, MNV1_EUNSUPPORTED, "pool: global average only (rows = cols = filtersize, kernel.cl:126)");
@@ -592,26 +664,26 @@ __global__ void widen_logits_kernel(float* out, const bf16* in, long n) {
 }
 
 int mnv1_softmax(mnv1_ctx* ctx, const mnv1_buf* logits, int classes, float* prob, int* top1, float* top1_prob) {
+  GUARD(ctx);
   if (!ctx || !logits || logits->is_u8 || logits->c != classes || logits->h != 1 || logits->w != 1)
     return fail(ctx, MNV1_EINVAL, "softmax: logits must be [n][classes][1][1]");
   const int n = logits->n;
   if (n == 0) return MNV1_OK;
-  float *d_logits = nullptr, *d_prob = nullptr, *d_p1 = nullptr;
-  int* d_top1 = nullptr;
-  cudaError_t e = cudaSuccess;
+  // one carve-up of the context's scratch: [logits fp32 (bf16 contexts)] [prob] [top1] [top1_prob]
   const long cnt = (long)n * classes;
+  const size_t b_logits = ctx->dtype == MNV1_BF16 ? (size_t)cnt * 4 : 0, b_prob = prob ? (size_t)cnt * 4 : 0;
+  uint8_t* base = (uint8_t*)scratch(ctx, b_logits + b_prob + (size_t)n * 8 + 64);
+  if (!base) return fail(ctx, MNV1_ENOMEM, "softmax: staging cudaMalloc failed");
+  float* d_logits = ctx->dtype == MNV1_BF16 ? (float*)base : (float*)logits->d;
+  float* d_prob = prob ? (float*)(base + b_logits) : nullptr;
+  int* d_top1 = (int*)(base + b_logits + b_prob);
+  float* d_p1 = (float*)(base + b_logits + b_prob + (size_t)n * 4);
+  cudaError_t e = cudaSuccess;
   if (ctx->dtype == MNV1_BF16) {
-    e = cudaMalloc(&d_logits, cnt * 4);
-    if (e == cudaSuccess) {
-      widen_logits_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(d_logits, (const bf16*)logits->d, cnt);
-      ctx->launches++;
-    }
-  } else {
-    d_logits = (float*)logits->d;
+    widen_logits_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(d_logits, (const bf16*)logits->d, cnt);
+    ctx->launches++;
+    e = cudaGetLastError();
   }
-  if (e == cudaSuccess && prob) e = cudaMalloc(&d_prob, cnt * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&d_top1, n * 4);
-  if (e == cudaSuccess) e = cudaMalloc(&d_p1, n * 4);
   if (e == cudaSuccess) {
     TimedLaunch tl(ctx);
     ctx->launches++; ctx->last_kernel = "softmax_kernel";
@@ -621,8 +693,6 @@ int mnv1_softmax(mnv1_ctx* ctx, const mnv1_buf* logits, int classes, float* prob
   if (e == cudaSuccess && top1) e = cudaMemcpyAsync(top1, d_top1, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess && top1_prob) e = cudaMemcpyAsync(top1_prob, d_p1, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (ctx->dtype == MNV1_BF16) cudaFree(d_logits);
-  cudaFree(d_prob); cudaFree(d_top1); cudaFree(d_p1);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "softmax");
   return MNV1_OK;
 }
@@ -638,6 +708,7 @@ int mnv1_layer_table(mnv1_layer_info* out) {
 }
 
 int mnv1_set_weights(mnv1_ctx* ctx, const float* weights, const float* scale, const float* shift, mnv1_act act) {
+  GUARD(ctx);
   if (!ctx || !weights) return fail(ctx, MNV1_EINVAL, "set_weights: null argument");
   const LayerDef* L = layer_defs();
   for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
@@ -656,6 +727,7 @@ int mnv1_set_weights(mnv1_ctx* ctx, const float* weights, const float* scale, co
 }
 
 int mnv1_load_weights(mnv1_ctx* ctx, const char* path, mnv1_act act) {
+  GUARD(ctx);
   if (!ctx || !path) return fail(ctx, MNV1_EINVAL, "load_weights: null argument");
   std::vector<float> w, sc, sh;
   std::string err;
@@ -692,10 +764,19 @@ int mnv1_read_ppm(const char* path, uint8_t* out, int height, int width) {
 static const size_t kImgBytes = 224 * 224 * 3;
 static const size_t kMaxActElems = 802816;  // layer 3 output per image (64 x 112 x 112)
 
+static int retire_all(mnv1_ctx* ctx);
+
 int mnv1_plan(mnv1_ctx* ctx, int max_batch) {
+  GUARD(ctx);
   if (!ctx || max_batch <= 0) return fail(ctx, MNV1_EINVAL, "plan: bad batch");
   if (max_batch <= ctx->plan_batch) return MNV1_OK;
-  cudaStreamSynchronize(ctx->stream);
+  // Re-planning frees the slot buffers: batches still in flight are completed first and their results
+  // delivered to the callers' arrays, so a later mnv1_forward_wait(ticket) finds them retired, not lost.
+  int rc = retire_all(ctx);
+  if (rc) return rc;
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  CK(ctx, cudaStreamSynchronize(ctx->d2h_stream));
   free_plan(ctx);
   const size_t act_bytes = (size_t)max_batch * kMaxActElems * elem_size(ctx->dtype);
   cudaError_t e = cudaSuccess;
@@ -801,6 +882,7 @@ static int check_ready(mnv1_ctx* ctx, int n) {
 }
 
 int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images, int n, void* d_logits, void* d_top1, void* d_prob) {
+  GUARD(ctx);
   int rc = check_ready(ctx, n);
   if (rc) return rc;
   if (!d_images || !d_logits) return fail(ctx, MNV1_EINVAL, "forward_device: images and logits are required");
@@ -838,6 +920,7 @@ int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images, int n, void* d_logi
 }
 
 int mnv1_ctx_use_fused_blocks(mnv1_ctx* ctx, int on) {
+  GUARD(ctx);
   if (!ctx) return MNV1_EINVAL;
   ctx->use_fused = on != 0;
   for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
@@ -849,6 +932,7 @@ int mnv1_ctx_use_fused_blocks(mnv1_ctx* ctx, int on) {
 // shape has no fused variant): out [n][cout][rows/stride][cols/stride]
 int mnv1_dw_pw_block(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_filter* dw, const mnv1_filter* pw,
                      int rows, int cols, int stride) {
+  GUARD(ctx);
   if (!ctx || !out || !in || !dw || !pw) return fail(ctx, MNV1_EINVAL, "dw_pw_block: null argument");
   if (dw->kind != MNV1_DEPTHWISE || pw->kind != MNV1_POINTWISE || pw->cin != dw->cout)
     return fail(ctx, MNV1_EINVAL, "dw_pw_block: filter mismatch");
@@ -870,6 +954,7 @@ int mnv1_dw_pw_block(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv
 
 // fused[i] = 1 when mnv1_forward* runs layer i+1 (a depthwise) and the pointwise after it as one kernel
 int mnv1_fused_layers(mnv1_ctx* ctx, int* fused) {
+  GUARD(ctx);
   if (!ctx || !fused) return fail(ctx, MNV1_EINVAL, "fused_layers: null argument");
   if (!ctx->have_weights) return fail(ctx, MNV1_ESTATE, "weights not loaded (mnv1_set_weights / mnv1_load_weights)");
   const LayerDef* L = layer_defs();
@@ -883,6 +968,7 @@ int mnv1_fused_layers(mnv1_ctx* ctx, int* fused) {
 }
 
 int mnv1_ctx_use_graph(mnv1_ctx* ctx, int on) {
+  GUARD(ctx);
   if (!ctx) return MNV1_EINVAL;
   ctx->use_graph = on != 0;
   return MNV1_OK;
@@ -904,8 +990,17 @@ static int finish_slot(mnv1_ctx* ctx, mnv1_ctx::Slot& sl) {
   return MNV1_OK;
 }
 
+static int retire_all(mnv1_ctx* ctx) {
+  for (auto& sl : ctx->slots) {
+    int rc = finish_slot(ctx, sl);
+    if (rc) return rc;
+  }
+  return MNV1_OK;
+}
+
 int mnv1_forward_submit(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int* top1, float* top1_prob,
                         long* ticket) {
+  GUARD(ctx);
   int rc = check_ready(ctx, n);
   if (rc) return rc;
   if (!images || !ticket) return fail(ctx, MNV1_EINVAL, "forward_submit: images / ticket is null");
@@ -945,15 +1040,17 @@ int mnv1_forward_submit(mnv1_ctx* ctx, const uint8_t* images, int n, float* logi
 }
 
 int mnv1_forward_wait(mnv1_ctx* ctx, long ticket) {
+  GUARD(ctx);
   if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
-  if (ticket < 0 || !ctx) return fail(ctx, MNV1_EINVAL, "forward_wait: unknown ticket");
+  if (ticket < 0) return fail(ctx, MNV1_EINVAL, "forward_wait: unknown ticket");
   mnv1_ctx::Slot& sl = ctx->slots[ticket % mnv1_ctx::kSlots];
   if (ticket < 0 || ticket >= ctx->next_ticket) return fail(ctx, MNV1_EINVAL, "forward_wait: unknown ticket");
-  if (sl.ticket != ticket) return MNV1_OK;  // already retired by a later submit
+  if (sl.ticket != ticket) return MNV1_OK;  // already retired (results delivered) by a later submit or a re-plan
   return finish_slot(ctx, sl);
 }
 
 int mnv1_forward(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int* top1, float* top1_prob) {
+  GUARD(ctx);
   long ticket = -1;
   int rc = mnv1_forward_submit(ctx, images, n, logits, top1, top1_prob, &ticket);
   if (rc) return rc;
@@ -961,11 +1058,12 @@ int mnv1_forward(mnv1_ctx* ctx, const uint8_t* images, int n, float* logits, int
 }
 
 int mnv1_forward_upto(mnv1_ctx* ctx, const uint8_t* images, int n, int last_layer, float* host_nchw) {
+  GUARD(ctx);
   int rc = check_ready(ctx, n);
   if (rc) return rc;
   if (!images || !host_nchw || last_layer < 1 || last_layer > MNV1_NUM_LAYERS)
     return fail(ctx, MNV1_EINVAL, "forward_upto: bad arguments");
-  for (auto& sl : ctx->slots) if ((rc = finish_slot(ctx, sl)) != MNV1_OK) return rc;
+  if ((rc = retire_all(ctx)) != MNV1_OK) return rc;
   CK(ctx, cudaMemcpyAsync(ctx->d_images, images, (size_t)n * kImgBytes, cudaMemcpyHostToDevice, ctx->stream));
   const void* res = nullptr;
   CK(ctx, enqueue_layers(ctx, ctx->d_images, n, last_layer, ctx->d_logits, ctx->d_top1, ctx->d_prob, &res, nullptr));
@@ -982,6 +1080,7 @@ int mnv1_forward_upto(mnv1_ctx* ctx, const uint8_t* images, int n, int last_laye
 }
 
 int mnv1_profile_layers(mnv1_ctx* ctx, const void* d_images, int n, int iters, float* times_ms) {
+  GUARD(ctx);
   int rc = check_ready(ctx, n);
   if (rc) return rc;
   if (!d_images || !times_ms || iters <= 0) return fail(ctx, MNV1_EINVAL, "profile_layers: bad arguments");
@@ -1006,6 +1105,7 @@ int mnv1_profile_layers(mnv1_ctx* ctx, const void* d_images, int n, int iters, f
 }
 
 int mnv1_synth_images_device(mnv1_ctx* ctx, void* d_images, int n, long first, uint64_t seed) {
+  GUARD(ctx);
   if (!ctx || !d_images || n < 0 || first < 0) return fail(ctx, MNV1_EINVAL, "synth_images: bad arguments");
   ctx->launches++; ctx->last_kernel = "synth_images_kernel";
   CK(ctx, mnv1::launch_synth_images((uint8_t*)d_images, first * (long)kImgBytes, (long)n * (long)kImgBytes, seed,

@@ -71,6 +71,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t p) { return __uint_as_float(p << 16); }
 __device__ __forceinline__ float bf16hi_to_f32(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
 
+// Pipeline stamps and experiment switches inside the kernels exist only in the MNV1_TRACE build
+// (`make trace` -> libmnv1_trace.so, read by tools/*_trace.py); the shipped library compiles them out.
+#ifdef MNV1_TRACE
+#define MNV1_DBG(x) (x)
+#define MNV1_TRC(x) (x)
+#else
+#define MNV1_DBG(x) 0
+#define MNV1_TRC(x) ((unsigned long long*)nullptr)
+#endif
+
 // ---- launchers implemented in the .cu files (all asynchronous on `st`) -------------------
 namespace mnv1 {
 
@@ -80,6 +90,17 @@ namespace mnv1 {
 // own prologue — barrier init, TMEM allocation, tensor-map prefetch, constants — so the launch latency
 // and the prologue of layer k+1 hide under the tail of layer k.  MNV1_NO_PDL=1 turns the attribute off.
 bool pdl_enabled();
+// Environment switches (fall back to the previous kernel of a layer; timing experiments): read ONCE per
+// process, by the first mnv1_ctx_create — never from a launch path.
+struct Switches { bool no_pdl, no_pair, no_cw, no_stem_rows, no_fused_head, no_fused_pair; long rb_mask; };
+const Switches& switches();
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remembered per (function,
+// current device), thread-safe, so that a second context on another GPU of the same process opts in too.
+cudaError_t ensure_dyn_smem(const void* fn, int bytes);
+inline bool capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};

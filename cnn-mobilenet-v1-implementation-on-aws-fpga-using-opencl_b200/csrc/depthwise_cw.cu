@@ -159,12 +159,10 @@ cudaError_t launch_cw(bf16* out, const bf16* in, const float* w, const float* sh
   if (items >= (1L << 31) || (long)n * Cfg::HI * Cfg::WI * Cfg::CP >= (1L << 31)) return cudaErrorNotSupported;
   const long grid = (items + Cfg::THREADS - 1) / Cfg::THREADS;
   const uint32_t cap2 = act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)depthwise_cw_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)depthwise_cw_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  {
+    cudaError_t e = ensure_dyn_smem((const void*)depthwise_cw_kernel<Cfg, true>, (int)Cfg::SMEM);
+    if (e == cudaSuccess) e = ensure_dyn_smem((const void*)depthwise_cw_kernel<Cfg, false>, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   if (act != MNV1_ACT_NONE)
     return launch_pdl(depthwise_cw_kernel<Cfg, true>, dim3((unsigned)grid), dim3(Cfg::THREADS), Cfg::SMEM, st,

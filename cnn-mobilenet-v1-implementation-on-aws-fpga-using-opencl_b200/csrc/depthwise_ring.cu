@@ -229,12 +229,10 @@ cudaError_t launch_dr(bf16* out, const bf16* in, const float* taps, const float*
   p.pad_lo = pad_lo;
   p.units = n * Cfg::BANDS * Cfg::STRIPS * Cfg::NKB;
   int grid = num_sms < p.units ? num_sms : p.units;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(depthwise_ring_kernel<Cfg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(depthwise_ring_kernel<Cfg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+  {
+    cudaError_t e = ensure_dyn_smem((const void*)depthwise_ring_kernel<Cfg, true>, (int)Cfg::SMEM);
+    if (e == cudaSuccess) e = ensure_dyn_smem((const void*)depthwise_ring_kernel<Cfg, false>, (int)Cfg::SMEM);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   if (act != MNV1_ACT_NONE) return launch_pdl(depthwise_ring_kernel<Cfg, true>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, st, tin, p);
   return launch_pdl(depthwise_ring_kernel<Cfg, false>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM, st, tin, p);

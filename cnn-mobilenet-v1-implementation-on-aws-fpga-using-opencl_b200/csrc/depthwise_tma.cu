@@ -332,12 +332,9 @@ cudaError_t launch_variant2(const bf16* in, DwParams p, int num_sms, cudaStream_
   if (stages < 2) return cudaErrorNotSupported;
   p.stages = stages;
   const size_t smem = 1024 + (size_t)stages * STAGE_PITCH + 16 * DT_MAX_STAGES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(depthwise_tma_kernel<S, CB, TWO, TW, RC, RELU>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  {
+    cudaError_t e = ensure_dyn_smem((const void*)depthwise_tma_kernel<S, CB, TWO, TW, RC, RELU>, 112 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   return launch_pdl(depthwise_tma_kernel<S, CB, TWO, TW, RC, RELU>, dim3((unsigned)grid), dim3(DT_THREADS), smem, st, tm, p);
 }

@@ -141,9 +141,9 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     mbar_init(b_full, 1);
     mbar_init_fence();
   }
-  if (p.trace && blockIdx.x == 0 && tid == 0) {           // debug: SM clock vs wall clock over the kernel
+  if (MNV1_TRC(p.trace) && blockIdx.x == 0 && tid == 0) {           // debug: SM clock vs wall clock over the kernel
     unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    p.trace[(7 * 128 + 0) * 4 + 0] = clock64(); p.trace[(7 * 128 + 0) * 4 + 1] = gt;
+    MNV1_TRC(p.trace)[(7 * 128 + 0) * 4 + 0] = clock64(); MNV1_TRC(p.trace)[(7 * 128 + 0) * 4 + 1] = gt;
   }
   if (warp == W_MMA) tmem_alloc(tmem_slot, 512u);
   tc_fence_before();
@@ -187,7 +187,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
               mbar_wait(in_empty + 8u * st, phase[g] ^ 1u);
               mbar_expect_tx(in_full + 8u * st, Cfg::CHUNK_BYTES);
               tma_load_4d(sIn + st * Cfg::CHUNK_PITCH, &tmap_in, in_full + 8u * st, cc[g], cx[g], cy[g] + k * RC, ci[g]);
-              if (k == 0) rb_stamp(p.trace, 0, u0 + g, 0); else if (k == NCHK - 1) rb_stamp(p.trace, 0, u0 + g, 1);
+              if (k == 0) rb_stamp(MNV1_TRC(p.trace), 0, u0 + g, 0); else if (k == NCHK - 1) rb_stamp(MNV1_TRC(p.trace), 0, u0 + g, 1);
               if (++stage[g] == NIG) { stage[g] = 0; phase[g] ^= 1u; }
             }
           }
@@ -209,16 +209,16 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
 #pragma unroll 1
         for (int kb = 0; kb < NKB; ++kb, ++ul) {
           const uint32_t st = (uint32_t)ul % NA, ph = ((uint32_t)ul / NA) & 1u;
-          rb_stamp(p.trace, 1, ul, 0);
+          rb_stamp(MNV1_TRC(p.trace), 1, ul, 0);
           mbar_wait(a_full + 8u * st, ph);
           tc_fence_after();
-          rb_stamp(p.trace, 1, ul, 1);
+          rb_stamp(MNV1_TRC(p.trace), 1, ul, 1);
           const uint64_t da = umma_desc_sw128(sA + st * RB_A_BYTES);
           const uint64_t db = umma_desc_sw128(sB + kb * Cfg::B_BYTES);
 #pragma unroll
           for (int k = 0; k < CK / 16; ++k) umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
           umma_commit(a_empty + 8u * st);
-          rb_stamp(p.trace, 1, ul, 2);
+          rb_stamp(MNV1_TRC(p.trace), 1, ul, 2);
         }
         umma_commit(tm_full + 8u * acc);
       }
@@ -242,26 +242,26 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       const uint32_t img = tile / (uint32_t)per_img, rem = tile - img * (uint32_t)per_img;
       const uint32_t band = rem / (uint32_t)p.strips, strip = rem - band * (uint32_t)p.strips;
       const uint32_t acc = (uint32_t)lt % NACC;
-      if (tracer) rb_stamp(p.trace, 2, lt, 0);
+      if (tracer) rb_stamp(MNV1_TRC(p.trace), 2, lt, 0);
       mbar_wait(tm_full + 8u * acc, ((uint32_t)lt / NACC) & 1u);
       tc_fence_after();
-      if (tracer) rb_stamp(p.trace, 2, lt, 1);
+      if (tracer) rb_stamp(MNV1_TRC(p.trace), 2, lt, 1);
 #pragma unroll
       for (int b = 0; b < COUT / 64; ++b, ++blk) {
         const uint32_t sbuf = wbuf + (NSTG == 1 ? 0u : (blk % NSTG) * 4096u);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)COUT + (uint32_t)(b * 64);
         uint32_t v[32];
-        if (!(p.dbg & 4)) tmem_ld32_nowait(taddr, v);
+        if (!(MNV1_DBG(p.dbg) & 4)) tmem_ld32_nowait(taddr, v);
         if (lane == 0) tma_store_wait_read<NSTG - 1>();      // the store that last read this buffer is done with it
         __syncwarp();
-        if (!(p.dbg & 4)) {
+        if (!(MNV1_DBG(p.dbg) & 4)) {
           // two 32-column halves through one set of 32 registers (the kernel is capped at 96 registers:
           // 18 warps are allocated as 20); scale / shift are compile-time offsets into the constant bank
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
-            if (tracer && b == 0 && half == 0) rb_stamp(p.trace, 6, lt, 0);
+            if (tracer && b == 0 && half == 0) rb_stamp(MNV1_TRC(p.trace), 6, lt, 0);
             tmem_ld_wait();
-            if (tracer && b == 0 && half == 0) rb_stamp(p.trace, 6, lt, 1);
+            if (tracer && b == 0 && half == 0) rb_stamp(MNV1_TRC(p.trace), 6, lt, 1);
             uint32_t q[16];
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
@@ -277,11 +277,11 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
               if (valid) sts128(sbuf + line_off + (((uint32_t)(half * 4 + c4) ^ line_x) << 4), q[4 * c4], q[4 * c4 + 1], q[4 * c4 + 2], q[4 * c4 + 3]);
           }
         }
-        if (tracer && b == 0) rb_stamp(p.trace, 6, lt, 2);
+        if (tracer && b == 0) rb_stamp(MNV1_TRC(p.trace), 6, lt, 2);
         fence_proxy_async();
         __syncwarp();
-        if (tracer && b == 0) rb_stamp(p.trace, 6, lt, 3);
-        if (lane == 0 && !(p.dbg & 2)) {
+        if (tracer && b == 0) rb_stamp(MNV1_TRC(p.trace), 6, lt, 3);
+        if (lane == 0 && !(MNV1_DBG(p.dbg) & 2)) {
           // the warp's two tile rows as one box (64 channels x TWO columns x 2 rows; smem = 2 x [16][64]
           // bf16, 128B swizzle), or the single-row box when the tile has an odd number of rows
           const int y = (int)band * R + row0;
@@ -293,7 +293,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tm_empty + 8u * acc);
-      if (tracer) rb_stamp(p.trace, 2, lt, 2);
+      if (tracer) rb_stamp(MNV1_TRC(p.trace), 2, lt, 2);
     }
     if (lane == 0) tma_store_wait_all();
   } else {
@@ -336,7 +336,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       const uint32_t dstA = sA + ast * RB_A_BYTES;
 
       const bool tracer = t == 0;
-      if (tracer) rb_stamp(p.trace, 3 + g, ul / NG, 0);
+      if (tracer) rb_stamp(MNV1_TRC(p.trace), 3 + g, ul / NG, 0);
       f32x2 acc[RING][TW][2];
       // The raw bf16 quads of input row q+1 are fetched while row q is being computed (one row of
       // software pipelining: without it every row exposes the ld.shared latency to its FFMAs).
@@ -347,7 +347,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
           prev_stage = cur_stage;
           cur_stage = (uint32_t)(g * NIG) + rstage;
           mbar_wait_relaxed(in_full + 8u * cur_stage, rphase);
-          if (q == 0 && tracer) rb_stamp(p.trace, 3 + g, ul / NG, 1);
+          if (q == 0 && tracer) rb_stamp(MNV1_TRC(p.trace), 3 + g, ul / NG, 1);
           rowbase = sIn + cur_stage * Cfg::CHUNK_PITCH + in_off;
           if (++rstage == NIG) { rstage = 0; rphase ^= 1u; }
         }
@@ -380,7 +380,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
                                        f2_fma(x[c * S + 1][v], w[3 * tr + 1][v], f2_fma(x[c * S][v], w[3 * tr][v], init)));
               }
             if (tr == 2) {                                  // output row o is complete
-              if (o == 0) { mbar_wait_relaxed(a_empty + 8u * ast, aph ^ 1u); if (tracer) rb_stamp(p.trace, 3 + g, ul / NG, 2); }   // the MMAs that last read this A stage retired
+              if (o == 0) { mbar_wait_relaxed(a_empty + 8u * ast, aph ^ 1u); if (tracer) rb_stamp(MNV1_TRC(p.trace), 3 + g, ul / NG, 2); }   // the MMAs that last read this A stage retired
               if (active) {
 #pragma unroll
                 for (int c = 0; c < TW; ++c)
@@ -394,15 +394,15 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full + 8u * ast);
-      if (tracer) rb_stamp(p.trace, 3 + g, ul / NG, 3);
+      if (tracer) rb_stamp(MNV1_TRC(p.trace), 3 + g, ul / NG, 3);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.trace && blockIdx.x == 0 && tid == 0) {
+  if (MNV1_TRC(p.trace) && blockIdx.x == 0 && tid == 0) {
     unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    p.trace[(7 * 128 + 0) * 4 + 2] = clock64(); p.trace[(7 * 128 + 0) * 4 + 3] = gt;
+    MNV1_TRC(p.trace)[(7 * 128 + 0) * 4 + 2] = clock64(); MNV1_TRC(p.trace)[(7 * 128 + 0) * 4 + 3] = gt;
   }
   if (warp == W_MMA) {
     tc_fence_after();
@@ -449,25 +449,25 @@ cudaError_t launch_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
   p.pw_cap2 = pw->act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
   p.bands = Ho / Cfg::R; p.strips = Wo / Cfg::TWO; p.pad_lo = pad_lo;
   p.tiles = (long)n * p.bands * p.strips;
+#ifdef MNV1_TRACE   // libmnv1_trace.so only (make trace)
   p.dbg = getenv("MNV1_RB_DBG") ? atoi(getenv("MNV1_RB_DBG")) : 0;
   static unsigned long long* d_trace = nullptr;
-  const bool tracing = getenv("MNV1_RB_TRACE") != nullptr;
+  const bool tracing = !capturing(st) && getenv("MNV1_RB_TRACE") != nullptr;
   if (tracing) {
     if (!d_trace) cudaMalloc(&d_trace, 8 * 128 * 4 * 8);
     cudaMemsetAsync(d_trace, 0, 8 * 128 * 4 * 8, st);
     p.trace = d_trace;
   }
+#endif
   const bool dr = dw->act != MNV1_ACT_NONE, pr = pw->act != MNV1_ACT_NONE;
   long grid = num_sms;
   if (grid > p.tiles) grid = p.tiles;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     cudaError_t e = cudaSuccess;
-    auto set = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM); };
+    auto set = [&](const void* f) { if (e == cudaSuccess) e = ensure_dyn_smem((const void*)f, (int)Cfg::SMEM); };
     set((const void*)fused_rb_kernel<Cfg, true, true>); set((const void*)fused_rb_kernel<Cfg, true, false>);
     set((const void*)fused_rb_kernel<Cfg, false, true>); set((const void*)fused_rb_kernel<Cfg, false, false>);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   cudaError_t le;
 #define RB_LAUNCH(A, B) le = launch_pdl(fused_rb_kernel<Cfg, A, B>, dim3((unsigned)grid), dim3(Cfg::THREADS), Cfg::SMEM, st, tin, pw->tmap_b, tout, tout2, p)
@@ -475,12 +475,14 @@ cudaError_t launch_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
   else    { if (pr) RB_LAUNCH(false, true); else RB_LAUNCH(false, false); }
 #undef RB_LAUNCH
   if (le != cudaSuccess) return le;
+#ifdef MNV1_TRACE
   if (tracing) {   // debug only: dump the stamps of the last launch
     std::vector<unsigned long long> h(8 * 128 * 4);
     cudaStreamSynchronize(st);
     cudaMemcpy(h.data(), d_trace, h.size() * 8, cudaMemcpyDeviceToHost);
     if (FILE* f = fopen(getenv("MNV1_RB_TRACE"), "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
   }
+#endif
   return cudaGetLastError();
 }
 
@@ -497,8 +499,7 @@ namespace {
 // index of the variant that handles this block, or -1
 int rb_variant(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride) {
   if (!dw->w_scaled || !pw->has_tmap || pw->cin != dw->cout || pw->tmap_bn != pw->cout) return -1;
-  // MNV1_RB_MASK (debug): bit i enables the i-th variant below; default all
-  static const long mask = getenv("MNV1_RB_MASK") ? strtol(getenv("MNV1_RB_MASK"), nullptr, 0) : ~0L;
+  const long mask = switches().rb_mask;   // MNV1_RB_MASK: bit i enables the i-th variant below; default all
   const int c = dw->cout, co = pw->cout;
 #define RB_IS(CFG, HW, BIT) \
   if ((mask >> BIT & 1) && stride == CFG::S && c == CFG::C && co == CFG::COUT && rows == HW && cols == HW && \

@@ -249,12 +249,10 @@ cudaError_t launch_fc(float* out, const float* pooled, const float* w_f32, const
   dim3 grid((classes + FC_CLS - 1) / FC_CLS, (n + FC_IMGS - 1) / FC_IMGS);
   const size_t smem = (size_t)FC_IMGS * k * sizeof(float);
   if (k % 256 || smem > 96 * 1024) return cudaErrorNotSupported;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fc_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fc_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  {
+    cudaError_t e = ensure_dyn_smem((const void*)fc_kernel<bf16>, 96 * 1024);
+    if (e == cudaSuccess) e = ensure_dyn_smem((const void*)fc_kernel<float>, 96 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   if (smem > 96 * 1024) return cudaErrorNotSupported;
   if (w_bf16 && k % (32 * FCM_WARPS) == 0) {   // bf16 filter: tensor cores, exact fp32 activations (three bf16 pieces)

@@ -96,18 +96,18 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0 && !(p.dbg & 2)) {
+    if (lane == 0 && !(MNV1_DBG(p.dbg) & 2)) {
       const uint32_t full_leader = mapa_shared(full, 0);
       int stage = 0; uint32_t phase = 0;
       for (long u = cid; u < num_units; u += num_clusters) {
         const int m_idx = (int)((u / n_tiles) * 2 + rank) * 128;
         for (int kb = 0; kb < num_kb; ++kb) {
-          if (kb == 0) pp_stamp(p.trace, 0, u / num_clusters, 0);
+          if (kb == 0) pp_stamp(MNV1_TRC(p.trace), 0, u / num_clusters, 0);
           mbar_wait(empty + 8u * stage, phase ^ 1u);       // the pair's MMAs that read this slot have retired
           const uint32_t sa = sRing + (uint32_t)stage * MC_STAGE_BYTES;
           if (rank == 0) mbar_expect_tx(full + 8u * stage, 2 * MC_STAGE_BYTES);   // both CTAs' bytes complete on the leader's barrier
           tma_load_2d_pair(sa, &tmap_a, full_leader + 8u * stage, kb * MC_BK, m_idx);
-          if (kb == num_kb - 1) pp_stamp(p.trace, 0, u / num_clusters, 2);
+          if (kb == num_kb - 1) pp_stamp(MNV1_TRC(p.trace), 0, u / num_clusters, 2);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -119,15 +119,15 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
     for (long u = cid; rank == 0 && u < num_units; u += num_clusters) {   // the leader issues for the pair
-      if (elected) pp_stamp(p.trace, 1, u / num_clusters, 0);
+      if (elected) pp_stamp(MNV1_TRC(p.trace), 1, u / num_clusters, 0);
       mbar_wait(tm_empty + 8u * as, aphase ^ 1u);          // epilogue has drained this accumulator stage
       tc_fence_after();
-      if (elected) pp_stamp(p.trace, 1, u / num_clusters, 1);
+      if (elected) pp_stamp(MNV1_TRC(p.trace), 1, u / num_clusters, 1);
       const uint32_t tmem_d = tmem_base + (uint32_t)as * MC_ACC_COLS;
       for (int kb = 0; kb < num_kb; ++kb) {
-        if (!(p.dbg & 2)) mbar_wait(full + 8u * stage, phase);
+        if (!(MNV1_DBG(p.dbg) & 2)) mbar_wait(full + 8u * stage, phase);
         tc_fence_after();
-        if (kb == 0 && elected) pp_stamp(p.trace, 1, u / num_clusters, 2);
+        if (kb == 0 && elected) pp_stamp(MNV1_TRC(p.trace), 1, u / num_clusters, 2);
         const uint32_t sa = sRing + (uint32_t)stage * MC_STAGE_BYTES;
         const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + MC_A_BYTES);
 #pragma unroll
@@ -136,14 +136,14 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         if (++stage == stages) { stage = 0; phase ^= 1u; }
       }
       umma_commit_pair_if(elected, tm_full + 8u * as);                     // both CTAs' accumulators are complete
-      if (elected) pp_stamp(p.trace, 1, u / num_clusters, 3);
+      if (elected) pp_stamp(MNV1_TRC(p.trace), 1, u / num_clusters, 3);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   } else if (warp == MC_W_BPROD) {
     // ================= filter producer =================
     // Its bytes are counted by the leader's expect_tx (a complete_tx that lands first only makes the
     // count negative for a while: the phase cannot complete before that arrival).
-    if (lane == 0 && !(p.dbg & 2)) {
+    if (lane == 0 && !(MNV1_DBG(p.dbg) & 2)) {
       const uint32_t full_leader = mapa_shared(full, 0);
       int stage = 0; uint32_t phase = 0;
       for (long u = cid; u < num_units; u += num_clusters) {
@@ -177,10 +177,10 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     for (long u = cid; u < num_units; u += num_clusters) {
       const int m_idx = (int)((u / n_tiles) * 2 + rank) * 128 + quarter * 32;
       const int n_idx = (int)(u % n_tiles) * 256;
-      if (threadIdx.x == 64) pp_stamp(p.trace, 2, u / num_clusters, 0);
+      if (threadIdx.x == 64) pp_stamp(MNV1_TRC(p.trace), 2, u / num_clusters, 0);
       mbar_wait(tm_full + 8u * as, aphase);
       tc_fence_after();
-      if (threadIdx.x == 64) pp_stamp(p.trace, 2, u / num_clusters, 1);
+      if (threadIdx.x == 64) pp_stamp(MNV1_TRC(p.trace), 2, u / num_clusters, 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * MC_ACC_COLS;
 #pragma unroll 1
       for (int b = h; b < 4; b += 2) {
@@ -205,8 +205,8 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             q[2 * j + 1] = pack2<RELU>(fmaf(__uint_as_float(v[4 * j + 2]), s4[j].z, t4[j].z), fmaf(__uint_as_float(v[4 * j + 3]), s4[j].w, t4[j].w), p.cap2);
           }
           if (half == 0) tmem_ld32_nowait(taddr + (uint32_t)(b * 64 + 32), v);   // second half under the stores
-          if (p.dbg & 4) {
-          } else if (p.dbg & 1) {
+          if (MNV1_DBG(p.dbg) & 4) {
+          } else if (MNV1_DBG(p.dbg) & 1) {
             const long row = (long)m_idx + lane;
             if (row < p.M) {
               uint4* gp = reinterpret_cast<uint4*>(p.out + row * p.Cout + n_idx + b * 64 + half * 32);
@@ -219,7 +219,7 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             sts128(sbuf + row_off + (((uint32_t)(4 * half + c4) ^ row_x) << 4), q[4 * c4], q[4 * c4 + 1], q[4 * c4 + 2], q[4 * c4 + 3]);
           }
         }
-        if (p.dbg & 5) continue;
+        if (MNV1_DBG(p.dbg) & 5) continue;
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {   // box = 64 columns x 32 rows; rows past M are clipped by the TMA unit
@@ -230,7 +230,7 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tm_empty_leader + 8u * as);
-      if (threadIdx.x == 64) pp_stamp(p.trace, 2, u / num_clusters, 2);
+      if (threadIdx.x == 64) pp_stamp(MNV1_TRC(p.trace), 2, u / num_clusters, 2);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
     if (lane == 0) tma_store_wait_all();
@@ -264,8 +264,7 @@ cudaError_t encode_box(CUtensorMap* map, const void* base, uint64_t rows, uint64
 // cudaErrorNotSupported (nothing launched) when the shape has no cluster variant.
 cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* f, long m, int k, int cout, int num_sms,
                                 cudaStream_t st, std::string* err) {
-  static const bool off = getenv("MNV1_NO_PAIR") != nullptr;   // debug switch: fall back to pointwise_tc_kernel
-  if (off || !f->w_bf16 || cout % 256 || k % MC_BK || k < 256 || cout > 1024 || num_sms < 2) return cudaErrorNotSupported;
+  if (switches().no_pair || !f->w_bf16 || cout % 256 || k % MC_BK || k < 256 || cout > 1024 || num_sms < 2) return cudaErrorNotSupported;
   if (m <= 0) return cudaSuccess;
   CUtensorMap ta, tb, to;
   cudaError_t e = encode_box(&ta, in, (uint64_t)m, (uint64_t)k, 128, err);
@@ -277,26 +276,26 @@ cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* 
   if (stages > MC_MAX_STAGES) stages = MC_MAX_STAGES;
   if (stages < 2) return cudaErrorNotSupported;
   const size_t smem = fixed + (size_t)stages * MC_STAGE_BYTES;
-  static bool attr_set = false;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(pointwise_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(pointwise_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  {
+    e = ensure_dyn_smem((const void*)pointwise_pair_kernel<true>, 227 * 1024);
+    if (e == cudaSuccess) e = ensure_dyn_smem((const void*)pointwise_pair_kernel<false>, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   McParams p{};
   p.scale = f->scale; p.shift = f->shift;
   p.cap2 = f->act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
   p.M = m; p.K = k; p.Cout = cout; p.stages = stages;
   p.out = out;
+#ifdef MNV1_TRACE   // experiment switches / pipeline stamps exist in libmnv1_trace.so only (make trace)
   { static const char* de = getenv("MNV1_PP_DBG"); p.dbg = de ? atoi(de) : 0; }
   static unsigned long long* d_trace_buf = nullptr;
-  const char* trace_path = getenv("MNV1_PW_TRACE");
+  const char* trace_path = capturing(st) ? nullptr : getenv("MNV1_PW_TRACE");
   if (trace_path) {
     if (!d_trace_buf) cudaMalloc(&d_trace_buf, 4 * 128 * 4 * 8);
     cudaMemsetAsync(d_trace_buf, 0, 4 * 128 * 4 * 8, st);
     p.trace = d_trace_buf;
   }
+#endif
   const long m_tiles = (m + 127) / 128, units = ((m_tiles + 1) / 2) * (cout / 256);
   long clusters = num_sms / 2;
   if (clusters > units) clusters = units;
@@ -313,12 +312,14 @@ cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* 
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   e = f->act != MNV1_ACT_NONE ? cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<true>, ta, tb, to, p)
                               : cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<false>, ta, tb, to, p);
-  if (trace_path && e == cudaSuccess) {   // debug only: dump the stamps of this launch
+#ifdef MNV1_TRACE
+  if (trace_path && e == cudaSuccess) {   // dump the stamps of this launch
     std::vector<unsigned long long> hbuf(4 * 128 * 4);
     cudaStreamSynchronize(st);
     cudaMemcpy(hbuf.data(), d_trace_buf, hbuf.size() * 8, cudaMemcpyDeviceToHost);
     if (FILE* fp = fopen(trace_path, "wb")) { fwrite(hbuf.data(), 8, hbuf.size(), fp); fclose(fp); }
   }
+#endif
   return e;
 }
 

@@ -238,7 +238,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0 && !(dbg & 2)) {
+    if (lane == 0 && !(MNV1_DBG(dbg) & 2)) {
       if (RESB) {  // the filter is loaded once: every k-block of the single n-tile
         mbar_expect_tx(&bars->resb_full, (uint32_t)num_kb * B_BYTES);
         for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(s_resb + (size_t)kb * B_BYTES, &tmap_b, &bars->resb_full, kb * TC_BK, 0);
@@ -250,13 +250,13 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         for (int g = 0; g < group && mt0 + g < m_tiles; ++g) {
           const int m_idx = (int)(mt0 + g) * TC_BM;
           for (int kb = 0; kb < num_kb; ++kb) {
-            if (kb == 0 && g == 0) pw_stamp(trace, 0, u / gridDim.x, 0);
+            if (kb == 0 && g == 0) pw_stamp(MNV1_TRC(trace), 0, u / gridDim.x, 0);
             mbar_wait(&bars->empty[stage], phase ^ 1u);
             uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
             mbar_expect_tx(&bars->full[stage], STAGE_BYTES);
             tma_load_2d(sa, &tmap_a, &bars->full[stage], kb * TC_BK, m_idx);
             if (!RESB) tma_load_2d(sa + A_BYTES, &tmap_b, &bars->full[stage], kb * TC_BK, n_idx);
-            if (kb == num_kb - 1) pw_stamp(trace, 0, u / gridDim.x, 2);
+            if (kb == num_kb - 1) pw_stamp(MNV1_TRC(trace), 0, u / gridDim.x, 2);
             if (++stage == stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -269,21 +269,21 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t elected = elect_one();
       int stage = 0; uint32_t phase = 0;
       int as = 0; uint32_t aphase = 0;
-      if (RESB && !(dbg & 2)) { mbar_wait(&bars->resb_full, 0); tc_fence_after(); }
+      if (RESB && !(MNV1_DBG(dbg) & 2)) { mbar_wait(&bars->resb_full, 0); tc_fence_after(); }
       const uint32_t resb_u = smem_u32(s_resb);
       const uint32_t ring_u = smem_u32(smem);
       for (long u = blockIdx.x; u < num_units; u += gridDim.x) {
         const long mt0 = (u / n_tiles) * group;
-        if (elected) pw_stamp(trace, 1, u / gridDim.x, 0);
+        if (elected) pw_stamp(MNV1_TRC(trace), 1, u / gridDim.x, 0);
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1u);   // epilogue has drained this accumulator stage
         tc_fence_after();
-        if (elected) pw_stamp(trace, 1, u / gridDim.x, 1);
+        if (elected) pw_stamp(MNV1_TRC(trace), 1, u / gridDim.x, 1);
         for (int g = 0; g < group && mt0 + g < m_tiles; ++g) {
           const uint32_t tmem_d = tmem_base + (uint32_t)as * ACC_COLS + (uint32_t)(g * BN);
           for (int kb = 0; kb < num_kb; ++kb) {
-            if (!(dbg & 2)) mbar_wait(&bars->full[stage], phase);          // TMA bytes have landed
+            if (!(MNV1_DBG(dbg) & 2)) mbar_wait(&bars->full[stage], phase);          // TMA bytes have landed
             tc_fence_after();
-            if (kb == 0 && g == 0 && elected) pw_stamp(trace, 1, u / gridDim.x, 2);
+            if (kb == 0 && g == 0 && elected) pw_stamp(MNV1_TRC(trace), 1, u / gridDim.x, 2);
             const uint32_t sa = ring_u + (uint32_t)stage * STAGE_BYTES;
             const uint64_t da = make_smem_desc(sa);
             const uint64_t db = make_smem_desc(RESB ? resb_u + (uint32_t)kb * B_BYTES : sa + A_BYTES);
@@ -299,7 +299,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           }
         }
         umma_commit_if(elected, &bars->tmem_full[as]);     // accumulator stage complete -> epilogue
-        if (elected) pw_stamp(trace, 1, u / gridDim.x, 3);
+        if (elected) pw_stamp(MNV1_TRC(trace), 1, u / gridDim.x, 3);
         if (++as == 2) { as = 0; aphase ^= 1u; }
       }
     }
@@ -331,10 +331,10 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (long u = blockIdx.x; u < num_units; u += gridDim.x) {
       const long mt0 = (u / n_tiles) * group;
       const int n_idx = (int)(u % n_tiles) * BN;
-      if (threadIdx.x == 64) pw_stamp(trace, 2, u / gridDim.x, 0);
+      if (threadIdx.x == 64) pw_stamp(MNV1_TRC(trace), 2, u / gridDim.x, 0);
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
-      if (threadIdx.x == 64) pw_stamp(trace, 2, u / gridDim.x, 1);
+      if (threadIdx.x == 64) pw_stamp(MNV1_TRC(trace), 2, u / gridDim.x, 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * ACC_COLS + (uint32_t)(32 * half);
       const int nblk = group * (BN / 64);                // 64-column blocks in this accumulator stage
 #pragma unroll 1
@@ -376,7 +376,7 @@ pointwise_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
-      if (threadIdx.x == 64) pw_stamp(trace, 2, u / gridDim.x, 2);
+      if (threadIdx.x == 64) pw_stamp(MNV1_TRC(trace), 2, u / gridDim.x, 2);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -460,46 +460,48 @@ cudaError_t launch_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtens
   if (stages > want) stages = want;
   if (stages < 2) return cudaErrorInvalidValue;
   const size_t smem = fixed + stages * stage_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     cudaError_t e = cudaSuccess;
     auto set = [&](const void* fn) {
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e == cudaSuccess) e = ensure_dyn_smem((const void*)fn, 227 * 1024);
     };
     set((const void*)pointwise_tc_kernel<BN, true, true>);
     set((const void*)pointwise_tc_kernel<BN, true, false>);
     set((const void*)pointwise_tc_kernel<BN, false, true>);
     set((const void*)pointwise_tc_kernel<BN, false, false>);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const long m_tiles = (m + TC_BM - 1) / TC_BM;
   const long units = ((m_tiles + group - 1) / group) * n_tiles;
   const unsigned grid = (unsigned)(units < num_sms ? units : num_sms);
   const uint32_t cap2 = act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;  // bf16x2 (6, 6) or (+inf, +inf)
   const bool relu = act != MNV1_ACT_NONE;
-  // debug facilities: MNV1_PW_DBG=2 runs without loads (MMAs never wait), MNV1_PW_TRACE=<file> dumps CTA 0's stamps
-  static const int dbg = getenv("MNV1_PW_DBG") ? atoi(getenv("MNV1_PW_DBG")) : 0;
-  static unsigned long long* d_trace_buf = nullptr;
+  int dbg = 0;
   unsigned long long* d_trace = nullptr;
-  const char* trace_path = getenv("MNV1_PW_TRACE");
+#ifdef MNV1_TRACE   // libmnv1_trace.so only: MNV1_PW_DBG=2 runs without loads, MNV1_PW_TRACE=<file> dumps CTA 0's stamps
+  { static const int dbg_env = getenv("MNV1_PW_DBG") ? atoi(getenv("MNV1_PW_DBG")) : 0; dbg = dbg_env; }
+  static unsigned long long* d_trace_buf = nullptr;
+  const char* trace_path = capturing(st) ? nullptr : getenv("MNV1_PW_TRACE");
   if (trace_path) {
     if (!d_trace_buf) cudaMalloc(&d_trace_buf, 4 * 128 * 4 * 8);
     cudaMemsetAsync(d_trace_buf, 0, 4 * 128 * 4 * 8, st);
     d_trace = d_trace_buf;
   }
+#endif
   cudaError_t le;
 #define PW_LAUNCH(R, B) \
   le = launch_pdl(pointwise_tc_kernel<BN, R, B>, dim3(grid), dim3(TC_THREADS), smem, st, ta, tb, to, scale, shift, cap2, m, k, cout, stages, group, dbg, d_trace)
   if (relu) { if (resb) PW_LAUNCH(true, true); else PW_LAUNCH(true, false); }
   else      { if (resb) PW_LAUNCH(false, true); else PW_LAUNCH(false, false); }
 #undef PW_LAUNCH
+#ifdef MNV1_TRACE
   if (trace_path && le == cudaSuccess) {
     std::vector<unsigned long long> hbuf(4 * 128 * 4);
     cudaStreamSynchronize(st);
     cudaMemcpy(hbuf.data(), d_trace_buf, hbuf.size() * 8, cudaMemcpyDeviceToHost);
     if (FILE* f = fopen(trace_path, "wb")) { fwrite(hbuf.data(), 8, hbuf.size(), f); fclose(f); }
   }
+#endif
   return le;
 }
 

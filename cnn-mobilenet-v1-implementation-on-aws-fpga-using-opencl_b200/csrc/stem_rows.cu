@@ -317,12 +317,10 @@ cudaError_t launch_stem_rows(bf16* out, const StemArgs& a, const __half* wq_dev,
   if (smem > 75 * 1024) return cudaErrorNotSupported;   // 3 CTAs per SM
   long grid = (long)num_sms * 3;
   if (grid > p.tiles) grid = p.tiles;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)stem_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)stem_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 75 * 1024);
+  {
+    cudaError_t e = ensure_dyn_smem((const void*)stem_rows_kernel<true>, 75 * 1024);
+    if (e == cudaSuccess) e = ensure_dyn_smem((const void*)stem_rows_kernel<false>, 75 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   if (act != MNV1_ACT_NONE) return launch_pdl(stem_rows_kernel<true>, dim3((unsigned)grid), dim3(SR_THREADS), smem, st, tm, p);
   return launch_pdl(stem_rows_kernel<false>, dim3((unsigned)grid), dim3(SR_THREADS), smem, st, tm, p);

@@ -397,16 +397,14 @@ cudaError_t launch_stem_tc(bf16* out, const StemArgs& a, const __half* wq_dev, c
   long grid = (long)num_sms * 3;
   if (grid > tiles) grid = tiles;
   const bool relu = act != MNV1_ACT_NONE;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     cudaError_t e = cudaSuccess;
-    auto set = [&](const void* f) { if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); };
+    auto set = [&](const void* f) { if (e == cudaSuccess) e = ensure_dyn_smem((const void*)f, (int)smem); };
     set((const void*)stem_tc_kernel<1, true, true>); set((const void*)stem_tc_kernel<1, false, true>);
     set((const void*)stem_tc_kernel<2, true, true>); set((const void*)stem_tc_kernel<2, false, true>);
     set((const void*)stem_tc_kernel<1, true, false>); set((const void*)stem_tc_kernel<1, false, false>);
     set((const void*)stem_tc_kernel<2, true, false>); set((const void*)stem_tc_kernel<2, false, false>);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   // interleaved = one base pointer with g = r + 1, b = r + 2 and pixel stride 3
   const bool il = a.pix_stride == 3 && a.g == a.r + 1 && a.b == a.r + 2;
