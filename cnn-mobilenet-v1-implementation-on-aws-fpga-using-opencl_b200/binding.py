@@ -60,6 +60,10 @@ def lib() -> C.CDLL:
         L.mnv1_launch_count.argtypes = [C.c_void_p]
         L.mnv1_buf_device_ptr.restype = C.c_void_p
         L.mnv1_buf_device_ptr.argtypes = [C.c_void_p]
+        L.mnv1_dp_last_error.restype = C.c_char_p
+        L.mnv1_dp_last_error.argtypes = [C.c_void_p]
+        L.mnv1_dp_ctx.restype = C.c_void_p
+        L.mnv1_dp_ctx.argtypes = [C.c_void_p, C.c_int]
         _lib = L
     return _lib
 
@@ -293,8 +297,121 @@ class Context:
         self._ck(lib().mnv1_profile_layers(self.h, C.c_void_p(d_images), n, iters, _vp(t)))
         return t
 
+    # ---- logits gather of the data-parallel mode (peer stores from the head kernel)
+    def gather_create(self, world: int, rank: int, rows_per_rank: int):
+        self._ck(lib().mnv1_gather_create(self.h, world, rank, rows_per_rank))
+
+    def gather_attach(self, peer: "Context"):
+        self._ck(lib().mnv1_gather_attach(self.h, peer.h))
+
+    def gather_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(lib().mnv1_gather_export(self.h, buf))
+        return buf.raw
+
+    def gather_import(self, peer_rank: int, handle: bytes):
+        self._ck(lib().mnv1_gather_import(self.h, int(peer_rank), C.c_char_p(handle)))
+
+    def gather_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(lib().mnv1_gather_ptrs(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def gather_destroy(self):
+        self._ck(lib().mnv1_gather_destroy(self.h))
+
+    def profile_prefixes(self, d_images: int, n: int, iters: int = 21) -> np.ndarray:
+        """cum_ms[k-1]: median replay time of the graph of layers 1..k (-1 where no launch ends at layer k)."""
+        t = np.zeros(29, dtype=np.float32)
+        self._ck(lib().mnv1_profile_prefixes(self.h, C.c_void_p(d_images), n, iters, _vp(t)))
+        return t
+
     def synth_images_device(self, d_images: int, n: int, first: int, seed: int):
         self._ck(lib().mnv1_synth_images_device(self.h, C.c_void_p(d_images), n, C.c_long(first), C.c_uint64(seed)))
+
+
+class DataParallel:
+    """mnv1_dp_*: one process driving several GPUs (a context + worker thread per device, batch cut into
+    contiguous shards, logits gathered by peer stores of the head kernel)."""
+
+    def __init__(self, devices: Sequence[int], dtype: int = BF16, max_batch_per_gpu: int = 256):
+        self.h = C.c_void_p()
+        self.devices = list(devices)
+        self.rows = int(max_batch_per_gpu)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        rc = lib().mnv1_dp_create(arr, len(self.devices), int(dtype), self.rows, C.byref(self.h))
+        if rc:
+            raise Mnv1Error(rc, (lib().mnv1_dp_last_error(None) or b"").decode())
+
+    def _ck(self, rc: int):
+        if rc:
+            raise Mnv1Error(rc, (lib().mnv1_dp_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if self.h:
+            lib().mnv1_dp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def size(self) -> int:
+        return lib().mnv1_dp_size(self.h)
+
+    def ctx_handle(self, rank: int) -> int:
+        return lib().mnv1_dp_ctx(self.h, rank)
+
+    def set_pad_mode(self, pad: int):
+        self._ck(lib().mnv1_dp_set_pad_mode(self.h, int(pad)))
+
+    def set_input_transform(self, scale: float, bias: float):
+        self._ck(lib().mnv1_dp_set_input_transform(self.h, C.c_float(scale), C.c_float(bias)))
+
+    def set_weights(self, weights, scale=None, shift=None, act=ACT_RELU6):
+        weights, scale, shift = _f32(weights), _f32(scale), _f32(shift)
+        self._ck(lib().mnv1_dp_set_weights(self.h, _vp(weights), _vp(scale), _vp(shift), int(act)))
+
+    def forward(self, images_u8: np.ndarray):
+        images_u8 = np.ascontiguousarray(images_u8, dtype=np.uint8)
+        n = images_u8.shape[0]
+        logits = np.empty((n, NUM_CLASSES), dtype=np.float32)
+        top1 = np.empty(n, dtype=np.int32)
+        p1 = np.empty(n, dtype=np.float32)
+        self._ck(lib().mnv1_dp_forward(self.h, _vp(images_u8), n, _vp(logits), _vp(top1), _vp(p1)))
+        return logits, top1, p1
+
+    def forward_submit(self, images_ptr: int, n: int, logits_ptr: int, top1_ptr: int, prob_ptr: int) -> int:
+        t = C.c_long(-1)
+        self._ck(lib().mnv1_dp_forward_submit(self.h, C.c_void_p(images_ptr), n, C.c_void_p(logits_ptr or None),
+                                              C.c_void_p(top1_ptr or None), C.c_void_p(prob_ptr or None), C.byref(t)))
+        return t.value
+
+    def forward_wait(self, ticket: int):
+        self._ck(lib().mnv1_dp_forward_wait(self.h, C.c_long(ticket)))
+
+    def forward_device(self, d_images: Sequence[int], n_per_gpu: int):
+        arr = (C.c_void_p * len(d_images))(*d_images)
+        self._ck(lib().mnv1_dp_forward_device(self.h, arr, int(n_per_gpu)))
+
+    def gather_ptrs(self, rank: int):
+        """(logits, top1, top1_prob) device pointers of rank's gather block: [size * rows] rows each."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        rc = lib().mnv1_gather_ptrs(C.c_void_p(self.ctx_handle(rank)), C.byref(a), C.byref(b), C.byref(c))
+        if rc:
+            raise Mnv1Error(rc, "gather_ptrs")
+        return a.value, b.value, c.value
+
+
+def dp_shard(n: int, rank: int, world: int):
+    first, count = C.c_int(), C.c_int()
+    rc = lib().mnv1_dp_shard(n, rank, world, C.byref(first), C.byref(count))
+    if rc:
+        raise Mnv1Error(rc, "bad shard arguments")
+    return first.value, count.value
 
 
 def declared_symbols() -> Sequence[str]:

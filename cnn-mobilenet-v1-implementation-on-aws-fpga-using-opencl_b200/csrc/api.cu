@@ -1,6 +1,7 @@
 // api.cu — the C-ABI of include/mnv1.h: context, buffers, filters, the four kernel entry
 // points with kernel.cl's argument order, and the whole-network executor (activation arena +
 // CUDA graph) that replaces the 29 copy-pasted layer blocks of MobileNet.c:207-2763.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -151,7 +152,19 @@ struct mnv1_ctx {
   // per-layer loop of the host programs allocates nothing after its first pass
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // logits gather of the data-parallel mode (mnv1_gather_*): this rank's gather block, the peers' blocks it
+  // stores into, and the HeadGather handed to the head kernel
+  int g_world = 0, g_rank = 0, g_rows = 0;
+  uint8_t* g_block = nullptr;                 // [world*rows][1000] f32 | [world*rows] i32 | [world*rows] f32
+  void* g_peer[8] = {};                       // base of rank d's block as mapped into this process / device
+  bool g_peer_ipc[8] = {};
+  mnv1::HeadGather gather = {};
 };
+
+extern "C" {
+static void drop_graphs(mnv1_ctx* ctx);
+static void gather_release(mnv1_ctx* ctx);
+}
 
 static void* scratch(mnv1_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->scratch_bytes) return ctx->scratch;
@@ -256,6 +269,7 @@ int mnv1_ctx_destroy(mnv1_ctx* ctx) {
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->d2h_stream) cudaStreamSynchronize(ctx->d2h_stream);
   free_plan(ctx);
+  gather_release(ctx);
   cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_bytes = 0;
   for (auto& f : ctx->net) { if (f) mnv1_filter_destroy(ctx, f); f = nullptr; }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -858,7 +872,7 @@ static cudaError_t enqueue_layers(mnv1_ctx* ctx, const uint8_t* d_img, int n, in
       case MNV1_FC: {
         int nl = 0;
         e = mnv1::launch_head(ctx->dtype, cur, n, 49, 1024, f, ctx->d_pooled, d_logits, d_top1, d_prob,
-                              MNV1_NUM_CLASSES, ctx->stream, &nl);
+                              MNV1_NUM_CLASSES, ctx->gather, ctx->stream, &nl);
         ctx->launches += nl; ctx->last_kernel = "head";
         cur = d_logits;
         break;
@@ -886,6 +900,7 @@ int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images, int n, void* d_logi
   int rc = check_ready(ctx, n);
   if (rc) return rc;
   if (!d_images || !d_logits) return fail(ctx, MNV1_EINVAL, "forward_device: images and logits are required");
+  if (ctx->gather.n_dst && n > ctx->g_rows) return fail(ctx, MNV1_EINVAL, "forward: batch exceeds the gather block's rows_per_rank");
   if (!ctx->use_graph) {
     CK(ctx, enqueue_layers(ctx, (const uint8_t*)d_images, n, MNV1_NUM_LAYERS, (float*)d_logits, (int*)d_top1,
                            (float*)d_prob, nullptr, nullptr));
@@ -1101,6 +1116,164 @@ int mnv1_profile_layers(mnv1_ctx* ctx, const void* d_images, int n, int iters, f
   }
   for (auto& ev : evs) cudaEventDestroy(ev);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "profile_layers");
+  return MNV1_OK;
+}
+
+// ---------------------------------------------------------------- data-parallel logits gather
+static void drop_graphs(mnv1_ctx* ctx) {
+  for (auto& kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+  ctx->graphs.clear();
+}
+static size_t gather_bytes(int total_rows) { return (size_t)total_rows * (MNV1_NUM_CLASSES * 4 + 8); }
+static void gather_rebuild(mnv1_ctx* ctx) {
+  mnv1::HeadGather g{};
+  const long total = (long)ctx->g_world * ctx->g_rows;
+  for (int d = 0; d < ctx->g_world; ++d) {
+    uint8_t* base = (uint8_t*)ctx->g_peer[d];
+    if (!base) continue;
+    g.logits[g.n_dst] = (float*)base;
+    g.top1[g.n_dst] = (int*)(base + (size_t)total * MNV1_NUM_CLASSES * 4);
+    g.prob[g.n_dst] = (float*)(base + (size_t)total * (MNV1_NUM_CLASSES * 4 + 4));
+    ++g.n_dst;
+  }
+  g.row0 = (long)ctx->g_rank * ctx->g_rows;
+  ctx->gather = g;
+  drop_graphs(ctx);                                        // captured graphs carry the old pointers
+}
+static void gather_release(mnv1_ctx* ctx) {
+  for (int d = 0; d < 8; ++d) {
+    if (ctx->g_peer[d] && ctx->g_peer_ipc[d]) cudaIpcCloseMemHandle(ctx->g_peer[d]);
+    ctx->g_peer[d] = nullptr; ctx->g_peer_ipc[d] = false;
+  }
+  cudaFree(ctx->g_block); ctx->g_block = nullptr;
+  ctx->g_world = ctx->g_rank = ctx->g_rows = 0;
+  ctx->gather = mnv1::HeadGather{};
+}
+
+int mnv1_gather_create(mnv1_ctx* ctx, int world, int rank, int rows_per_rank) {
+  GUARD(ctx);
+  if (!ctx || world < 1 || world > 8 || rank < 0 || rank >= world || rows_per_rank <= 0)
+    return fail(ctx, MNV1_EINVAL, "gather_create: need 1 <= world <= 8, 0 <= rank < world, rows_per_rank > 0");
+  if (ctx->dtype != MNV1_BF16) return fail(ctx, MNV1_EUNSUPPORTED, "gather: bf16 contexts only (the cluster head kernel does the stores)");
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  gather_release(ctx);
+  cudaError_t e = cudaMalloc(&ctx->g_block, gather_bytes(world * rows_per_rank));
+  if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, std::string("gather_create: ") + cudaGetErrorString(e));
+  CK(ctx, cudaMemset(ctx->g_block, 0, gather_bytes(world * rows_per_rank)));
+  ctx->g_world = world; ctx->g_rank = rank; ctx->g_rows = rows_per_rank;
+  ctx->g_peer[rank] = ctx->g_block;
+  gather_rebuild(ctx);
+  return MNV1_OK;
+}
+int mnv1_gather_export(mnv1_ctx* ctx, void* handle64) {
+  GUARD(ctx);
+  if (!ctx || !handle64 || !ctx->g_block) return fail(ctx, MNV1_ESTATE, "gather_export: call mnv1_gather_create first");
+  static_assert(sizeof(cudaIpcMemHandle_t) == MNV1_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CK(ctx, cudaIpcGetMemHandle(&h, ctx->g_block));
+  memcpy(handle64, &h, sizeof h);
+  return MNV1_OK;
+}
+int mnv1_gather_import(mnv1_ctx* ctx, int peer_rank, const void* handle64) {
+  GUARD(ctx);
+  if (!ctx || !handle64 || !ctx->g_block || peer_rank < 0 || peer_rank >= ctx->g_world || peer_rank == ctx->g_rank)
+    return fail(ctx, MNV1_EINVAL, "gather_import: bad peer rank or no gather block");
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof h);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaIpcOpenMemHandle (is the peer GPU NVLink / P2P reachable?)");
+  if (ctx->g_peer[peer_rank] && ctx->g_peer_ipc[peer_rank]) cudaIpcCloseMemHandle(ctx->g_peer[peer_rank]);
+  ctx->g_peer[peer_rank] = p; ctx->g_peer_ipc[peer_rank] = true;
+  gather_rebuild(ctx);
+  return MNV1_OK;
+}
+int mnv1_gather_attach(mnv1_ctx* ctx, mnv1_ctx* peer) {
+  GUARD(ctx);
+  if (!ctx || !peer || !ctx->g_block || !peer->g_block || peer->g_world != ctx->g_world || peer->g_rows != ctx->g_rows ||
+      peer->g_rank == ctx->g_rank)
+    return fail(ctx, MNV1_EINVAL, "gather_attach: both contexts need gather blocks of the same geometry and different ranks");
+  if (peer->device != ctx->device) {
+    int can = 0;
+    CK(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, peer->device));
+    if (!can) return fail(ctx, MNV1_EUNSUPPORTED, "gather_attach: no peer access between the two devices");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    else if (e != cudaSuccess) return fail_cuda(ctx, e, "cudaDeviceEnablePeerAccess");
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->g_peer[peer->g_rank] = peer->g_block; ctx->g_peer_ipc[peer->g_rank] = false;
+  gather_rebuild(ctx);
+  return MNV1_OK;
+}
+int mnv1_gather_destroy(mnv1_ctx* ctx) {
+  GUARD(ctx);
+  if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  gather_release(ctx);
+  drop_graphs(ctx);
+  return MNV1_OK;
+}
+int mnv1_gather_ptrs(mnv1_ctx* ctx, void** logits, void** top1, void** top1_prob) {
+  if (!ctx || !ctx->g_block) return fail(ctx, MNV1_ESTATE, "gather_ptrs: no gather block");
+  const size_t total = (size_t)ctx->g_world * ctx->g_rows;
+  if (logits) *logits = ctx->g_block;
+  if (top1) *top1 = ctx->g_block + total * MNV1_NUM_CLASSES * 4;
+  if (top1_prob) *top1_prob = ctx->g_block + total * (MNV1_NUM_CLASSES * 4 + 4);
+  return MNV1_OK;
+}
+int mnv1_ctx_device(const mnv1_ctx* ctx) { return ctx ? ctx->device : -1; }
+
+// Per-launch device time INSIDE the replayed graph.  For every launch boundary k of the schedule the graph of
+// layers 1..k is captured and replayed `iters` times; cum_ms[k-1] is the median replay time (CUDA events on
+// the context stream), -1 for a layer that ends inside a fused launch (a depthwise fused with its pointwise,
+// the pool inside the head).  The difference of two consecutive boundaries is that launch's time with the
+// programmatic-launch overlap of the real step, and the differences add up to the whole step by construction.
+int mnv1_profile_prefixes(mnv1_ctx* ctx, const void* d_images, int n, int iters, float* cum_ms) {
+  GUARD(ctx);
+  int rc = check_ready(ctx, n);
+  if (rc) return rc;
+  if (!d_images || !cum_ms || iters <= 0) return fail(ctx, MNV1_EINVAL, "profile_prefixes: bad arguments");
+  int fused[MNV1_NUM_LAYERS];
+  if ((rc = mnv1_fused_layers(ctx, fused)) != MNV1_OK) return rc;
+  const LayerDef* L = layer_defs();
+  std::vector<cudaEvent_t> evs(iters + 1);
+  for (auto& e : evs) CK(ctx, cudaEventCreate(&e));
+  std::vector<float> t(iters);
+  cudaError_t e = cudaSuccess;
+  const long launches_before = ctx->launches;
+  for (int k = 1; k <= MNV1_NUM_LAYERS && e == cudaSuccess; ++k) {
+    cum_ms[k - 1] = -1.f;
+    if (fused[k - 1]) continue;                                               // ends inside a fused dw+pw launch
+    if (L[k - 1].kind == MNV1_POOL && ctx->dtype == MNV1_BF16) continue;       // pooled inside the head kernel
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) break;
+    cudaError_t e1 = enqueue_layers(ctx, (const uint8_t*)d_images, n, k, ctx->d_logits, ctx->d_top1, ctx->d_prob, nullptr, nullptr);
+    e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (e1 != cudaSuccess) e = e1;
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess) break;
+    for (int w = 0; w < 2 && e == cudaSuccess; ++w) e = cudaGraphLaunch(exec, ctx->stream);   // warm-up
+    for (int it = 0; it < iters && e == cudaSuccess; ++it) {
+      cudaEventRecord(evs[it], ctx->stream);
+      e = cudaGraphLaunch(exec, ctx->stream);
+    }
+    cudaEventRecord(evs[iters], ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) {
+      for (int it = 0; it < iters; ++it) cudaEventElapsedTime(&t[it], evs[it], evs[it + 1]);
+      std::sort(t.begin(), t.end());
+      cum_ms[k - 1] = t[iters / 2];
+    }
+    cudaGraphExecDestroy(exec);
+  }
+  ctx->launches = launches_before;
+  for (auto& ev : evs) cudaEventDestroy(ev);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "profile_prefixes");
   return MNV1_OK;
 }
 

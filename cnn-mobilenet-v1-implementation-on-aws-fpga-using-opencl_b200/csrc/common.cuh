@@ -166,10 +166,20 @@ cudaError_t launch_fused_dw_pw(bf16* out, const bf16* in, const mnv1_filter* dw,
 bool fused_dw_pw_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride);
 cudaError_t launch_pool(mnv1_dtype dt, void* out, const void* in, int n, int hw, int c, bool out_f32,
                         cudaStream_t st);
-// fused head: global average pool -> FC (+bias) -> softmax -> argmax
+// Logits gather without a collective kernel: the head kernel also stores every image's logits / top-1 /
+// top-1 probability into the gather buffers of up to 8 GPUs (own buffer included) at row `row0 + image`.
+// The pointers are peer-mapped (cudaDeviceEnablePeerAccess inside one process, CUDA IPC across processes).
+struct HeadGather {
+  float* logits[8];
+  int* top1[8];
+  float* prob[8];
+  int n_dst;
+  long row0;
+};
+// head: global average pool -> FC (+bias) -> softmax -> argmax (one cluster kernel on bf16 contexts)
 cudaError_t launch_head(mnv1_dtype dt, const void* in, int n, int hw, int c, const mnv1_filter* fc,
                         float* pooled_scratch, float* logits, int* top1, float* top1_prob,
-                        int classes, cudaStream_t st, int* launches);
+                        int classes, const HeadGather& gather, cudaStream_t st, int* launches);
 cudaError_t launch_softmax(const float* logits, int n, int classes, float* prob, int* top1,
                            float* top1_prob, cudaStream_t st);
 cudaError_t launch_nchw_to_nhwc(mnv1_dtype dt, void* out_nhwc, const float* in_nchw, int n, int c,

@@ -363,9 +363,208 @@ cudaError_t launch_softmax(const float* logits, int n, int classes, float* prob,
   return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fused head (bf16 contexts): pool -> FC -> softmax/argmax as ONE kernel on thread-block clusters.
+// A cluster of 8 CTAs owns 16 images.  The three stages need all-to-all data inside the group (the FC
+// contracts over all 1024 pooled channels of an image, softmax over all 1000 classes), so the stages are
+// separated by hardware cluster barriers (release / acquire: the small intermediate arrays travel through
+// L2) instead of kernel boundaries — two launch gaps and two grid ramps less (22 us -> ~8 us per batch):
+//   stage 1  CTA r pools images 2r, 2r+1: thread = 4 channels of one image, 49 independent 8-byte loads,
+//            the same summation order as pool_kernel (4 pixel phases, folded left to right) -> fp32 means
+//   stage 2  CTA r computes classes [125 r, 125 r + 125) for the 16 images with the exact 3-piece bf16
+//            split of fc_mma_kernel (16 warps = 4 class groups x 4 k-splits, folded in a fixed order)
+//   stage 3  CTA r: softmax / argmax of images 2r, 2r+1 (256 threads each, first maximum wins,
+//            MobileNet.c:2786), and the logits-gather: each row is also stored straight into the gather
+//            buffers of the peer GPUs (HeadGather: peer-mapped pointers over NVLink) — no collective kernel.
+constexpr int HF_CL = 8, HF_IMGS = 16, HF_THREADS = 512, HF_CLS = 125;
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(HF_CL, 1, 1) __launch_bounds__(HF_THREADS, 1)
+head_fused_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const float* __restrict__ bias,
+                  float* pooled, float* logits, int* __restrict__ top1, float* __restrict__ top1_prob, int n, int hw,
+                  int classes, const HeadGather g) {
+  constexpr int K = 1024;
+  __shared__ float s_part[4][4][16][33];     // [class group][k-split][image][class]
+  __shared__ float s_red[2][8];
+  __shared__ int s_arg[2][8];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int img_base = (int)(blockIdx.x / HF_CL) * HF_IMGS;
+  pdl_trigger();
+  pdl_wait();
+
+  // ---- stage 1: global average pool of this CTA's two images
+  {
+    const int img = img_base + 2 * (int)rank + (tid >> 8), q = tid & 255;
+    if (img < n) {
+      const bf16* p = in + (long)img * hw * K + 4 * q;
+      float s[4][4];
+#pragma unroll
+      for (int ph = 0; ph < 4; ++ph) s[ph][0] = s[ph][1] = s[ph][2] = s[ph][3] = 0.f;
+      // groups of 16 pixels: 16 independent 8-byte loads in flight, the phase (i & 3) a compile-time constant
+      for (int i0 = 0; i0 < hw; i0 += 16) {
+        uint2 v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = i0 + j < hw ? __ldg(reinterpret_cast<const uint2*>(p + (long)(i0 + j) * K)) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (i0 + j < hw) {
+            float* a = s[j & 3];
+            a[0] += bf16lo_to_f32(v[j].x); a[1] += bf16hi_to_f32(v[j].x); a[2] += bf16lo_to_f32(v[j].y); a[3] += bf16hi_to_f32(v[j].y);
+          }
+        }
+      }
+      const float inv = 1.0f / (float)hw;
+      float4 o;
+      o.x = (s[0][0] + s[1][0] + s[2][0] + s[3][0]) * inv; o.y = (s[0][1] + s[1][1] + s[2][1] + s[3][1]) * inv;
+      o.z = (s[0][2] + s[1][2] + s[2][2] + s[3][2]) * inv; o.w = (s[0][3] + s[1][3] + s[2][3] + s[3][3]) * inv;
+      *reinterpret_cast<float4*>(pooled + (long)img * K + 4 * q) = o;
+    }
+  }
+  cluster_barrier();
+
+  // ---- stage 2: FC for classes [cls_lo, cls_lo + 125) x 16 images
+  const int cls_lo = (int)rank * HF_CLS, cls_hi = min(cls_lo + HF_CLS, classes);
+  {
+    const int cg = warp >> 2, ks = warp & 3, gq = lane >> 2, t = lane & 3;
+    const int cls0 = cls_lo + cg * 32;
+    const int r0 = min(img_base + gq, n - 1), r1 = min(img_base + gq + 8, n - 1);
+    const int k_lo = ks * (K / 4), k_hi = k_lo + K / 4;
+    const float* a0p = pooled + (long)r0 * K + 8 * t;
+    const float* a1p = pooled + (long)r1 * K + 8 * t;
+    const bf16* bp[FCM_NT];
+#pragma unroll
+    for (int j = 0; j < FCM_NT; ++j) bp[j] = w + (long)min(cls0 + 8 * j + gq, classes - 1) * K + 8 * t;
+    float acc[FCM_NT][4];
+#pragma unroll
+    for (int j = 0; j < FCM_NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    float4 an[4];
+    uint4 bn[FCM_NT];
+    auto load = [&](int kb) {
+      // the pooled means were written by other SMs of the cluster in this kernel: plain (coherent) loads
+      an[0] = *reinterpret_cast<const float4*>(a0p + kb); an[1] = *reinterpret_cast<const float4*>(a0p + kb + 4);
+      an[2] = *reinterpret_cast<const float4*>(a1p + kb); an[3] = *reinterpret_cast<const float4*>(a1p + kb + 4);
+#pragma unroll
+      for (int j = 0; j < FCM_NT; ++j) bn[j] = __ldg(reinterpret_cast<const uint4*>(bp[j] + kb));
+    };
+    load(k_lo);
+    for (int kb = k_lo; kb < k_hi; kb += 32) {
+      const float4 a00 = an[0], a01 = an[1], a10 = an[2], a11 = an[3];
+      uint4 b[FCM_NT];
+#pragma unroll
+      for (int j = 0; j < FCM_NT; ++j) b[j] = bn[j];
+      if (kb + 32 < k_hi) load(kb + 32);
+      uint32_t ah[2][4], am[2][4], al[2][4];
+      split3(a00.x, a00.y, ah[0][0], am[0][0], al[0][0]); split3(a10.x, a10.y, ah[0][1], am[0][1], al[0][1]);
+      split3(a00.z, a00.w, ah[0][2], am[0][2], al[0][2]); split3(a10.z, a10.w, ah[0][3], am[0][3], al[0][3]);
+      split3(a01.x, a01.y, ah[1][0], am[1][0], al[1][0]); split3(a11.x, a11.y, ah[1][1], am[1][1], al[1][1]);
+      split3(a01.z, a01.w, ah[1][2], am[1][2], al[1][2]); split3(a11.z, a11.w, ah[1][3], am[1][3], al[1][3]);
+#pragma unroll
+      for (int j = 0; j < FCM_NT; ++j) {
+        mma_bf16_16816(acc[j], al[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], al[1], b[j].z, b[j].w);   // small pieces first
+        mma_bf16_16816(acc[j], am[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], am[1], b[j].z, b[j].w);
+        mma_bf16_16816(acc[j], ah[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], ah[1], b[j].z, b[j].w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < FCM_NT; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s_part[cg][ks][gq + 8 * (e >> 1)][8 * j + 2 * t + (e & 1)] = acc[j][e];
+  }
+  __syncthreads();
+  for (int i = tid; i < 4 * 16 * 32; i += HF_THREADS) {
+    const int cg = i >> 9, r = (i >> 5) & 15, c = i & 31;
+    const int img = img_base + r, cls = cls_lo + cg * 32 + c;
+    if (img < n && cls < cls_hi)
+      logits[(long)img * classes + cls] =
+          ((s_part[cg][0][r][c] + s_part[cg][1][r][c]) + (s_part[cg][2][r][c] + s_part[cg][3][r][c])) + (bias ? __ldg(bias + cls) : 0.f);
+  }
+  cluster_barrier();
+
+  // ---- stage 3: softmax / argmax of this CTA's two images (+ the gather stores)
+  {
+    const int sub = tid >> 8, t = tid & 255, w8 = (tid >> 5) & 7;
+    const int img = img_base + 2 * (int)rank + sub;
+    const bool live = img < n;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = t + i * 256;
+      v[i] = (live && k < classes) ? logits[(long)img * classes + k] : -INFINITY;
+    }
+    for (int d = 0; d < g.n_dst; ++d) {          // peer GPUs' gather buffers (row = global image index)
+      float* dst = g.logits[d] + (g.row0 + img) * (long)classes;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const int k = t + i * 256; if (live && k < classes) dst[k] = v[i]; }
+    }
+    float mx = -INFINITY;
+    int arg = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (v[i] > mx) { mx = v[i]; arg = t + i * 256; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float omx = __shfl_xor_sync(0xffffffffu, mx, off);
+      const int oarg = __shfl_xor_sync(0xffffffffu, arg, off);
+      if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
+    }
+    if (lane == 0) { s_red[sub][w8] = mx; s_arg[sub][w8] = arg; }
+    __syncthreads();
+    mx = s_red[sub][0]; arg = s_arg[sub][0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k)
+      if (s_red[sub][k] > mx || (s_red[sub][k] == mx && s_arg[sub][k] < arg)) { mx = s_red[sub][k]; arg = s_arg[sub][k]; }
+    __syncthreads();
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sum += __expf(v[i] - mx);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (lane == 0) s_red[sub][w8] = sum;
+    __syncthreads();
+    if (t == 0 && live) {
+      sum = ((s_red[sub][0] + s_red[sub][1]) + (s_red[sub][2] + s_red[sub][3])) + ((s_red[sub][4] + s_red[sub][5]) + (s_red[sub][6] + s_red[sub][7]));
+      const float p1 = 1.0f / sum;
+      if (top1) top1[img] = arg;
+      if (top1_prob) top1_prob[img] = p1;
+      for (int d = 0; d < g.n_dst; ++d) {
+        if (g.top1[d]) g.top1[d][g.row0 + img] = arg;
+        if (g.prob[d]) g.prob[d][g.row0 + img] = p1;
+      }
+    }
+  }
+}
+
+cudaError_t launch_head_fused(const bf16* in, int n, int hw, int c, const mnv1_filter* fc, float* pooled_scratch,
+                              float* logits, int* top1, float* top1_prob, int classes, const HeadGather& g,
+                              cudaStream_t st) {
+  if (c != 1024 || classes > HF_CL * HF_CLS || !fc->w_bf16 || switches().no_fused_head) return cudaErrorNotSupported;
+  if (n <= 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(((n + HF_IMGS - 1) / HF_IMGS) * HF_CL));
+  cfg.blockDim = dim3(HF_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, head_fused_kernel, in, (const bf16*)fc->w_bf16, (const float*)fc->shift, pooled_scratch,
+                            logits, top1, top1_prob, n, hw, classes, g);
+}
+
 cudaError_t launch_head(mnv1_dtype dt, const void* in, int n, int hw, int c, const mnv1_filter* fc,
                         float* pooled_scratch, float* logits, int* top1, float* top1_prob, int classes,
-                        cudaStream_t st, int* launches) {
+                        const HeadGather& g, cudaStream_t st, int* launches) {
+  if (dt == MNV1_BF16) {
+    cudaError_t fe = launch_head_fused((const bf16*)in, n, hw, c, fc, pooled_scratch, logits, top1, top1_prob, classes, g, st);
+    if (fe != cudaErrorNotSupported) { if (launches) *launches = 1; return fe; }
+  }
+  if (g.n_dst) return cudaErrorNotSupported;   // the peer gather lives in the fused kernel only
   cudaError_t e = launch_pool(dt, pooled_scratch, in, n, hw, c, /*out_f32=*/true, st);
   if (e != cudaSuccess) return e;
   e = launch_fc(logits, pooled_scratch, fc->w_f32, dt == MNV1_BF16 ? fc->w_bf16 : nullptr, fc->shift, n, c, classes, st);

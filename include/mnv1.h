@@ -161,6 +161,11 @@ int mnv1_forward_upto(mnv1_ctx* ctx, const uint8_t* images, int n, int last_laye
                       float* host_nchw);
 /* per-layer device time (ms) of the last mnv1_profile_layers run; times[29] */
 int mnv1_profile_layers(mnv1_ctx* ctx, const void* d_images_u8, int n, int iters, float* times_ms);
+/* per-launch device time inside the replayed CUDA graph: cum_ms[k-1] = median time of the graph of layers
+ * 1..k over `iters` replays, for every k at which a launch of the schedule ends (-1 elsewhere: a depthwise
+ * fused with its pointwise, the pool inside the head kernel).  Consecutive differences are per-launch times
+ * that add up to the whole step; what MobileNet.c:303-305,315 printed per layer, without the host round trip. */
+int mnv1_profile_prefixes(mnv1_ctx* ctx, const void* d_images_u8, int n, int iters, float* cum_ms29);
 /* fill d_images (u8 [n][224][224][3]) with the synthetic stream of SURVEY §8(d): images
  * first..first+n-1 of seed `seed`, generated on the device */
 int mnv1_synth_images_device(mnv1_ctx* ctx, void* d_images_u8, int n, long first, uint64_t seed);
@@ -188,6 +193,51 @@ int mnv1_ctx_use_graph(mnv1_ctx* ctx, int on);
 int mnv1_host_alloc(size_t bytes, void** out);
 int mnv1_host_free(void* p);
 const char* mnv1_version(void);
+
+/* ---- data parallelism over the batch (BASELINE config 5).  The reference is batch 1 on one
+ *      queue (MobileNet.c:29,171); images are independent, so the batch is cut into contiguous shards,
+ *      one context per GPU, weights replicated, no collective on the data path.  The only exchange is the
+ *      logits gather, and it is done by the head kernel itself: every rank stores its rows straight into
+ *      the gather blocks of all ranks through peer-mapped pointers over NVLink (no collective kernel). --- */
+#define MNV1_IPC_HANDLE_BYTES 64
+/* allocate this rank's gather block: rows [world * rows_per_rank] of logits[1000] f32, top1 i32, top1_prob f32;
+ * from now on mnv1_forward* on this context (n <= rows_per_rank) also writes rows rank*rows_per_rank + i of
+ * every attached / imported block.  bf16 contexts. */
+int mnv1_gather_create(mnv1_ctx* ctx, int world, int rank, int rows_per_rank);
+/* peers in the SAME process (cudaDeviceEnablePeerAccess): make ctx store into peer's block */
+int mnv1_gather_attach(mnv1_ctx* ctx, mnv1_ctx* peer);
+/* peers in OTHER processes (one process per GPU): exchange the 64-byte CUDA IPC handle by any means */
+int mnv1_gather_export(mnv1_ctx* ctx, void* handle64);
+int mnv1_gather_import(mnv1_ctx* ctx, int peer_rank, const void* handle64);
+/* device pointers of this rank's gathered arrays; complete once every rank's forward has finished */
+int mnv1_gather_ptrs(mnv1_ctx* ctx, void** d_logits, void** d_top1, void** d_top1_prob);
+int mnv1_gather_destroy(mnv1_ctx* ctx);
+int mnv1_ctx_device(const mnv1_ctx* ctx);
+
+/* one process driving several GPUs: a context and a worker thread per device, the gather wired all-to-all */
+typedef struct mnv1_dp mnv1_dp;
+int mnv1_dp_create(const int* devices, int n_devices, mnv1_dtype dtype, int max_batch_per_gpu, mnv1_dp** dp);
+int mnv1_dp_destroy(mnv1_dp* dp);
+const char* mnv1_dp_last_error(const mnv1_dp* dp);
+int mnv1_dp_size(const mnv1_dp* dp);
+mnv1_ctx* mnv1_dp_ctx(mnv1_dp* dp, int rank); /* for per-context settings; do not destroy */
+int mnv1_dp_set_pad_mode(mnv1_dp* dp, mnv1_pad pad);
+int mnv1_dp_set_input_transform(mnv1_dp* dp, float scale, float bias);
+int mnv1_dp_set_weights(mnv1_dp* dp, const float* weights, const float* scale, const float* shift, mnv1_act act);
+int mnv1_dp_load_weights(mnv1_dp* dp, const char* path, mnv1_act act);
+/* shard of rank r of g for a batch of n: images [first, first + count) — contiguous, the remainder spread
+ * over the first ranks */
+int mnv1_dp_shard(int n, int rank, int world, int* first, int* count);
+/* host in / host out like mnv1_forward, the batch cut into contiguous shards; every GPU copies its shard of
+ * the outputs straight into the caller's arrays.  submit/wait as for mnv1_forward_submit/_wait. */
+int mnv1_dp_forward(mnv1_dp* dp, const uint8_t* images, int n, float* logits, int* top1, float* top1_prob);
+int mnv1_dp_forward_submit(mnv1_dp* dp, const uint8_t* images, int n, float* logits, int* top1, float* top1_prob,
+                           long* ticket);
+int mnv1_dp_forward_wait(mnv1_dp* dp, long ticket);
+/* device in / device out: rank r runs its n_per_gpu images (device pointer d_images[r], on device r);
+ * when this returns every rank's gather block (mnv1_gather_ptrs on mnv1_dp_ctx(dp, r)) holds all
+ * world * n_per_gpu rows. */
+int mnv1_dp_forward_device(mnv1_dp* dp, const void* const* d_images, int n_per_gpu);
 
 #ifdef __cplusplus
 }

@@ -164,3 +164,19 @@ def test_bench_merges_fused_rows():
     want = (LAYERS[1].in_elems * 2 + LAYERS[2].out_elems * 2) * 256 + LAYERS[1].w_cnt * 4 + LAYERS[2].w_cnt * 2
     assert row["bytes"] == want and row["bytes"] < plain[1]["bytes"] + plain[2]["bytes"]
     assert abs(row["flops"] - (plain[1]["flops"] + plain[2]["flops"])) < 1.0
+
+
+def test_dp_shard_matches_python_sharding():
+    """mnv1_dp_shard (C-ABI, no GPU needed) == shard.shard_range: contiguous, remainder on the low ranks."""
+    from mnv1_b200 import shard
+    for n in (0, 1, 7, 256, 2048, 2049):
+        for world in (1, 2, 3, 4, 8):
+            cover = []
+            for r in range(world):
+                first, count = mn.dp_shard(n, r, world)
+                a, b = shard.shard_range(n, r, world)
+                assert (first, first + count) == (a, b)
+                cover += list(range(first, first + count))
+            assert cover == list(range(n))
+    with pytest.raises(mn.Mnv1Error):
+        mn.dp_shard(4, 2, 2)
