@@ -18,7 +18,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MNV1_LIB", os.path.join(PKG_DIR, "libmnv1.so"))  # MNV1_LIB: kernel experiments only
 HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "mnv1.h")
 
-F32, BF16 = 0, 1
+F32, BF16, U8 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
 PAD_REF, PAD_TFSAME = 0, 1
 CONVOLUTE, DEPTHWISE, POINTWISE, POOL, FC = 0, 1, 2, 3, 4
@@ -189,6 +189,22 @@ class Context:
         b = self.malloc(n, c, h, w)
         self._ck(lib().mnv1_upload_planar(self.h, b.h, _vp(arr)))
         return b
+
+    def upload_planar_u8(self, arr: np.ndarray) -> Buffer:
+        """integer contexts: planar u8 host array, the reference's own layout (MobileNet.c:116-143)"""
+        arr = np.ascontiguousarray(arr, dtype=np.uint8)
+        n, c, h, w = arr.shape
+        b = self.malloc(n, c, h, w)
+        self._ck(lib().mnv1_upload_planar_u8(self.h, b.h, _vp(arr)))
+        return b
+
+    def download_planar_u8(self, b: Buffer) -> np.ndarray:
+        out = np.empty(b.shape, dtype=np.uint8)
+        self._ck(lib().mnv1_download_planar_u8(self.h, b.h, _vp(out)))
+        return out
+
+    def set_u8_store(self, wrap: bool):
+        self._ck(lib().mnv1_ctx_set_u8_store(self.h, int(wrap)))
 
     def download_planar(self, b: Buffer) -> np.ndarray:
         out = np.empty(b.shape, dtype=np.float32)

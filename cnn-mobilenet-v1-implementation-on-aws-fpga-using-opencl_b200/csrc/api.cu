@@ -148,6 +148,7 @@ struct mnv1_ctx {
   std::map<GraphKey, cudaGraphExec_t> graphs;
   bool use_graph = true;
   bool use_fused = true;   // depthwise->pointwise block fusion inside mnv1_forward*
+  int u8_wrap = 0;         // integer contexts: 1 = wrap modulo 256 like kernel.cl's store to unsigned char, 0 = saturate
   // staging for the planar <-> NHWC boundary copies and mnv1_softmax: grown on demand, then reused, so the
   // per-layer loop of the host programs allocates nothing after its first pass
   void* scratch = nullptr;
@@ -192,7 +193,7 @@ static int fail_cuda(mnv1_ctx* ctx, cudaError_t e, const char* what) {
     if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);           \
   } while (0)
 
-static size_t elem_size(mnv1_dtype dt) { return dt == MNV1_BF16 ? 2 : 4; }
+static size_t elem_size(mnv1_dtype dt) { return dt == MNV1_BF16 ? 2 : dt == MNV1_U8 ? 1 : 4; }
 static int pad_lo_for(const mnv1_ctx* ctx, int stride) {
   return (stride == 2 && ctx->pad == MNV1_PAD_TFSAME) ? 0 : 1;
 }
@@ -214,7 +215,7 @@ const char* mnv1_version(void) { return "mnv1-b200 0.1 (sm_100a)"; }
 const char* mnv1_last_error(const mnv1_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
 int mnv1_ctx_create(int device, mnv1_dtype dtype, mnv1_ctx** out) {
-  if (!out || (dtype != MNV1_F32 && dtype != MNV1_BF16)) return fail(nullptr, MNV1_EINVAL, "bad ctx_create args");
+  if (!out || (dtype != MNV1_F32 && dtype != MNV1_BF16 && dtype != MNV1_U8)) return fail(nullptr, MNV1_EINVAL, "bad ctx_create args");
   *out = nullptr;
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -381,7 +382,9 @@ int mnv1_upload_planar(mnv1_ctx* ctx, mnv1_buf* b, const float* host) {
   float* stage = (float*)scratch(ctx, elems * 4);
   if (!stage) return fail(ctx, MNV1_ENOMEM, "staging cudaMalloc failed");
   cudaError_t e = cudaMemcpyAsync(stage, host, elems * 4, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = mnv1::launch_nchw_to_nhwc(ctx->dtype, b->d, stage, b->n, b->c, b->h, b->w, ctx->stream);
+  if (e == cudaSuccess)
+    e = ctx->dtype == MNV1_U8 ? mnv1::launch_u8_layout(0, b->d, stage, false, b->n, b->c, b->h * b->w, ctx->stream)
+                              : mnv1::launch_nchw_to_nhwc(ctx->dtype, b->d, stage, b->n, b->c, b->h, b->w, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   ctx->launches++;
   if (e != cudaSuccess) return fail_cuda(ctx, e, "upload_planar");
@@ -394,11 +397,51 @@ int mnv1_download_planar(mnv1_ctx* ctx, mnv1_buf* b, float* host) {
   const size_t elems = (size_t)b->n * b->c * b->h * b->w;
   float* stage = (float*)scratch(ctx, elems * 4);
   if (!stage) return fail(ctx, MNV1_ENOMEM, "staging cudaMalloc failed");
-  cudaError_t e = mnv1::launch_nhwc_to_nchw(ctx->dtype, stage, b->d, b->n, b->c, b->h, b->w, ctx->stream);
+  cudaError_t e = ctx->dtype == MNV1_U8 ? mnv1::launch_u8_layout(1, stage, b->d, false, b->n, b->c, b->h * b->w, ctx->stream)
+                                        : mnv1::launch_nhwc_to_nchw(ctx->dtype, stage, b->d, b->n, b->c, b->h, b->w, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(host, stage, elems * 4, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   ctx->launches++;
   if (e != cudaSuccess) return fail_cuda(ctx, e, "download_planar");
+  return MNV1_OK;
+}
+
+// planar u8 host arrays — the reference's own host layout (`unsigned char* output_image`, MobileNet.c:116-143,
+// written / read by clEnqueueWriteBuffer / ReadBuffer :350,:395) — without a detour through fp32
+int mnv1_upload_planar_u8(mnv1_ctx* ctx, mnv1_buf* b, const uint8_t* host) {
+  GUARD(ctx);
+  if (!ctx || !b || b->is_u8 || (!host && b->bytes)) return fail(ctx, MNV1_EINVAL, "bad upload_planar_u8");
+  if (ctx->dtype != MNV1_U8) return fail(ctx, MNV1_EUNSUPPORTED, "upload_planar_u8: integer (MNV1_U8) contexts only");
+  if (!b->bytes) return MNV1_OK;
+  const size_t elems = (size_t)b->n * b->c * b->h * b->w;
+  uint8_t* stage = (uint8_t*)scratch(ctx, elems);
+  if (!stage) return fail(ctx, MNV1_ENOMEM, "staging cudaMalloc failed");
+  cudaError_t e = cudaMemcpyAsync(stage, host, elems, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = mnv1::launch_u8_layout(0, b->d, stage, true, b->n, b->c, b->h * b->w, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  ctx->launches++;
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "upload_planar_u8");
+  return MNV1_OK;
+}
+int mnv1_download_planar_u8(mnv1_ctx* ctx, mnv1_buf* b, uint8_t* host) {
+  GUARD(ctx);
+  if (!ctx || !b || b->is_u8 || (!host && b->bytes)) return fail(ctx, MNV1_EINVAL, "bad download_planar_u8");
+  if (ctx->dtype != MNV1_U8) return fail(ctx, MNV1_EUNSUPPORTED, "download_planar_u8: integer (MNV1_U8) contexts only");
+  if (!b->bytes) return MNV1_OK;
+  const size_t elems = (size_t)b->n * b->c * b->h * b->w;
+  uint8_t* stage = (uint8_t*)scratch(ctx, elems);
+  if (!stage) return fail(ctx, MNV1_ENOMEM, "staging cudaMalloc failed");
+  cudaError_t e = mnv1::launch_u8_layout(1, stage, b->d, true, b->n, b->c, b->h * b->w, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(host, stage, elems, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  ctx->launches++;
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "download_planar_u8");
+  return MNV1_OK;
+}
+int mnv1_ctx_set_u8_store(mnv1_ctx* ctx, int wrap) {
+  if (!ctx) return fail(nullptr, MNV1_EINVAL, "null ctx");
+  ctx->u8_wrap = wrap ? 1 : 0;
+  drop_graphs(ctx);
   return MNV1_OK;
 }
 
@@ -416,12 +459,73 @@ static uint16_t f32_to_bf16_rne(float x) {
   return (uint16_t)(u >> 16);
 }
 
+// Integer contexts: the filter values must be integers in [-128, 127] (the reference's int8_t buffers,
+// MobileNet.c:116,248); `shift` is an integer bias added to the s32 accumulator; `scale`, when given, must be
+// the same power of two 2^-s for every channel and becomes the right shift s of the requantisation.
+static int create_filter_u8(mnv1_ctx* ctx, mnv1_filter* f, const float* w, const float* scale, const float* shift) {
+  const int cin = f->cin, cout = f->cout;
+  size_t cnt = 0;
+  switch (f->kind) {
+    case MNV1_CONVOLUTE: if (cin != 3 || cout != 32) return fail(ctx, MNV1_EUNSUPPORTED, "convolute (u8): 3 -> 32 channels only"); cnt = (size_t)27 * cout; break;
+    case MNV1_DEPTHWISE: if (cin != cout || cout % 4) return fail(ctx, MNV1_EINVAL, "depthwise (u8): cin == cout, a multiple of 4"); cnt = (size_t)9 * cout; break;
+    case MNV1_POINTWISE: case MNV1_FC: cnt = (size_t)cin * cout; break;
+    default: return fail(ctx, MNV1_EINVAL, "filter kind has no weights");
+  }
+  for (size_t i = 0; i < cnt; ++i)
+    if (w[i] != (float)(int)w[i] || w[i] < -128.f || w[i] > 127.f)
+      return fail(ctx, MNV1_EINVAL, "integer context: filter values must be integers in [-128, 127]");
+  if (scale) {
+    int s = 0;
+    while (s < 31 && scale[0] != 1.0f / (float)(1u << s)) ++s;
+    if (scale[0] != 1.0f / (float)(1u << s)) return fail(ctx, MNV1_EINVAL, "integer context: scale must be 2^-s, 0 <= s <= 31");
+    for (int c = 1; c < cout; ++c)
+      if (scale[c] != scale[0]) return fail(ctx, MNV1_EINVAL, "integer context: scale must be the same power of two for every channel");
+    f->rshift = s;
+  }
+  std::vector<int8_t> q(cnt);
+  std::vector<int> packed;
+  if (f->kind == MNV1_CONVOLUTE) {           // [O][3][3][3] -> 7 words of 4 taps per filter (28th tap = 0)
+    packed.assign((size_t)cout * 7, 0);
+    for (int o = 0; o < cout; ++o)
+      for (int t = 0; t < 27; ++t)
+        packed[(size_t)o * 7 + (t >> 2)] |= (int)((uint32_t)(uint8_t)(int8_t)(int)w[(size_t)o * 27 + t] << (8 * (t & 3)));
+  } else if (f->kind == MNV1_DEPTHWISE) {    // [C][3][3] -> [9][C]
+    for (int c = 0; c < cout; ++c)
+      for (int t = 0; t < 9; ++t) q[(size_t)t * cout + c] = (int8_t)(int)w[(size_t)c * 9 + t];
+  } else {
+    for (size_t i = 0; i < cnt; ++i) q[i] = (int8_t)(int)w[i];                 // [Cout][Cin]: the K-major B operand as is
+  }
+  if (!packed.empty()) {
+    if (cudaMalloc(&f->w_q32, packed.size() * 4) != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "cudaMalloc(filter) failed");
+    CK(ctx, cudaMemcpy(f->w_q32, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+  } else {
+    if (cudaMalloc(&f->w_s8, cnt) != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "cudaMalloc(filter) failed");
+    CK(ctx, cudaMemcpy(f->w_s8, q.data(), cnt, cudaMemcpyHostToDevice));
+  }
+  if (shift) {
+    std::vector<int> b(cout);
+    for (int c = 0; c < cout; ++c) {
+      if (shift[c] != (float)(int)shift[c]) return fail(ctx, MNV1_EINVAL, "integer context: shift (bias) must be integers");
+      b[c] = (int)shift[c];
+    }
+    if (cudaMalloc(&f->bias_i32, (size_t)cout * 4) != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "cudaMalloc(filter) failed");
+    CK(ctx, cudaMemcpy(f->bias_i32, b.data(), (size_t)cout * 4, cudaMemcpyHostToDevice));
+  }
+  return MNV1_OK;
+}
+
 int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, int cout, const float* scale,
                        const float* shift, mnv1_act act, mnv1_filter** out) {
   GUARD(ctx);
   if (!ctx || !w || !out || cin <= 0 || cout <= 0) return fail(ctx, MNV1_EINVAL, "bad filter_create args");
   std::unique_ptr<mnv1_filter> f(new mnv1_filter);
   f->kind = kind; f->cin = cin; f->cout = cout; f->act = act;
+  if (ctx->dtype == MNV1_U8) {
+    int rc8 = create_filter_u8(ctx, f.get(), w, scale, shift);
+    if (rc8) { mnv1_filter_destroy(ctx, f.release()); return rc8; }
+    *out = f.release();
+    return MNV1_OK;
+  }
   std::vector<float> dev;
   int rc = MNV1_OK;
   switch (kind) {
@@ -485,6 +589,7 @@ int mnv1_filter_destroy(mnv1_ctx* ctx, mnv1_filter* f) {
   if (!f) return MNV1_OK;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   cudaFree(f->w_f32); cudaFree(f->w_scaled); cudaFree(f->w_bf16); cudaFree(f->wq); cudaFree(f->shift2); cudaFree(f->scale); cudaFree(f->shift);
+  cudaFree(f->w_s8); cudaFree(f->w_q32); cudaFree(f->bias_i32);
   delete f;
   return MNV1_OK;
 }
@@ -509,6 +614,10 @@ static cudaError_t run_stem(mnv1_ctx* ctx, void* out, const uint8_t* r, const ui
   mnv1::StemArgs a{r, g, b, pix_stride, img_stride, n, rows, cols, stride, f->cout, pad_lo_for(ctx, stride),
                    ctx->in_scale, ctx->in_bias};
   ctx->launches++;
+  if (ctx->dtype == MNV1_U8) {
+    ctx->last_kernel = "stem_u8_kernel";
+    return mnv1::launch_stem_u8((uint8_t*)out, a, f, ctx->u8_wrap, ctx->stream);
+  }
   if (ctx->dtype == MNV1_BF16 && f->prepared && f->prep_scale == ctx->in_scale && f->prep_bias == ctx->in_bias) {
     ctx->err.clear();
     if (!mnv1::switches().no_stem_rows) {
@@ -526,6 +635,11 @@ static cudaError_t run_stem(mnv1_ctx* ctx, void* out, const uint8_t* r, const ui
 static cudaError_t run_depthwise(mnv1_ctx* ctx, void* out, const void* in, const mnv1_filter* f, int n, int rows,
                                  int cols, int stride) {
   ctx->launches++;
+  if (ctx->dtype == MNV1_U8) {
+    ctx->last_kernel = "depthwise_u8_kernel";
+    return mnv1::launch_depthwise_u8((uint8_t*)out, (const uint8_t*)in, f, n, rows, cols, stride, f->cout, pad_lo_for(ctx, stride),
+                                     ctx->u8_wrap, ctx->stream);
+  }
   if (ctx->dtype == MNV1_BF16 && f->w_scaled) {
     ctx->err.clear();
     if (!mnv1::switches().no_cw) {
@@ -549,6 +663,11 @@ static cudaError_t run_depthwise(mnv1_ctx* ctx, void* out, const void* in, const
 static cudaError_t run_pointwise(mnv1_ctx* ctx, void* out, const void* in, const mnv1_filter* f, long m,
                                  bool force_simt) {
   ctx->launches++;
+  if (ctx->dtype == MNV1_U8) {
+    ctx->last_kernel = "pointwise_i8_kernel";
+    ctx->err.clear();
+    return mnv1::launch_pointwise_i8((uint8_t*)out, (const uint8_t*)in, f, m, f->cin, f->cout, ctx->u8_wrap, ctx->stream, &ctx->err);
+  }
   if (ctx->dtype == MNV1_BF16 && f->has_tmap && !force_simt) {
     ctx->err.clear();
     cudaError_t ep = mnv1::launch_pointwise_pair((bf16*)out, (const bf16*)in, f, m, f->cin, f->cout, ctx->num_sms,
@@ -583,6 +702,8 @@ static int convolute_common(mnv1_ctx* ctx, mnv1_buf* out, const uint8_t* r, cons
   if (rc) return rc;
   const size_t plane = (size_t)rows * cols * pix_stride;
   if (avail_bytes < plane * out->n) return fail(ctx, MNV1_EINVAL, "convolute: image buffer too small for the batch");
+  if (ctx->dtype == MNV1_U8 && (ctx->in_scale != 1.f || ctx->in_bias != 0.f))
+    return fail(ctx, MNV1_EUNSUPPORTED, "convolute: integer contexts read the raw u8 pixels (input transform must be 1, 0)");
   rc = prepare_stem(ctx, const_cast<mnv1_filter*>(f));
   if (rc) return rc;
   TimedLaunch tl(ctx);
@@ -616,7 +737,7 @@ int mnv1_depthwise(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv1_
   if (filtersize != 3) return fail(ctx, MNV1_EUNSUPPORTED, "depthwise: only 3x3 (K = 3, MobileNet.c:15)");
   if ((stride != 1 && stride != 2) || rows % stride || cols % stride)
     return fail(ctx, MNV1_EUNSUPPORTED, "depthwise: stride must be 1 or 2 and divide rows/cols");
-  const int vec = ctx->dtype == MNV1_BF16 ? 8 : 4;
+  const int vec = ctx->dtype == MNV1_BF16 ? 8 : 4;   // u8: one 32-bit word
   if (op_size % vec) return fail(ctx, MNV1_EUNSUPPORTED, "depthwise: op_size must be a multiple of the 128-bit channel vector");
   int rc = check_fmap(ctx, in, op_size, rows, cols, "depthwise(in)");
   if (rc) return rc;
@@ -668,6 +789,11 @@ int mnv1_pool(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, int rows, int co
   if (in->n != out->n) return fail(ctx, MNV1_EINVAL, "pool: batch mismatch");
   TimedLaunch tl(ctx);
   ctx->launches++; ctx->last_kernel = "pool_kernel";
+  if (ctx->dtype == MNV1_U8) {
+    ctx->last_kernel = "pool_u8_kernel";
+    CK(ctx, mnv1::launch_pool_u8((uint8_t*)out->d, (const uint8_t*)in->d, in->n, rows * cols, op_size, ctx->u8_wrap, ctx->stream));
+    return MNV1_OK;
+  }
   CK(ctx, mnv1::launch_pool(ctx->dtype, out->d, in->d, in->n, rows * cols, op_size, false, ctx->stream));
   return MNV1_OK;
 }
@@ -685,10 +811,10 @@ int mnv1_softmax(mnv1_ctx* ctx, const mnv1_buf* logits, int classes, float* prob
   if (n == 0) return MNV1_OK;
   // one carve-up of the context's scratch: [logits fp32 (bf16 contexts)] [prob] [top1] [top1_prob]
   const long cnt = (long)n * classes;
-  const size_t b_logits = ctx->dtype == MNV1_BF16 ? (size_t)cnt * 4 : 0, b_prob = prob ? (size_t)cnt * 4 : 0;
+  const size_t b_logits = ctx->dtype != MNV1_F32 ? (size_t)cnt * 4 : 0, b_prob = prob ? (size_t)cnt * 4 : 0;
   uint8_t* base = (uint8_t*)scratch(ctx, b_logits + b_prob + (size_t)n * 8 + 64);
   if (!base) return fail(ctx, MNV1_ENOMEM, "softmax: staging cudaMalloc failed");
-  float* d_logits = ctx->dtype == MNV1_BF16 ? (float*)base : (float*)logits->d;
+  float* d_logits = ctx->dtype != MNV1_F32 ? (float*)base : (float*)logits->d;
   float* d_prob = prob ? (float*)(base + b_logits) : nullptr;
   int* d_top1 = (int*)(base + b_logits + b_prob);
   float* d_p1 = (float*)(base + b_logits + b_prob + (size_t)n * 4);
@@ -697,6 +823,9 @@ int mnv1_softmax(mnv1_ctx* ctx, const mnv1_buf* logits, int classes, float* prob
     widen_logits_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(d_logits, (const bf16*)logits->d, cnt);
     ctx->launches++;
     e = cudaGetLastError();
+  } else if (ctx->dtype == MNV1_U8) {     // the reference's softmax runs over the u8 logits (MobileNet.c:2769-2781)
+    e = mnv1::launch_u8_to_f32(d_logits, (const uint8_t*)logits->d, cnt, ctx->stream);
+    ctx->launches++;
   }
   if (e == cudaSuccess) {
     TimedLaunch tl(ctx);
@@ -730,7 +859,8 @@ int mnv1_set_weights(mnv1_ctx* ctx, const float* weights, const float* scale, co
   for (int i = 0; i < MNV1_NUM_LAYERS; ++i) {
     if (ctx->net[i]) { mnv1_filter_destroy(ctx, ctx->net[i]); ctx->net[i] = nullptr; }
     if (L[i].kind == MNV1_POOL) continue;
-    const bool fc = L[i].kind == MNV1_FC;
+    // integer contexts: the reference's FC is its `pointwise` kernel, ReLU and requantisation included (MobileNet.c:2689-2754)
+    const bool fc = L[i].kind == MNV1_FC && ctx->dtype != MNV1_U8;
     int rc = mnv1_filter_create(ctx, (mnv1_kind)L[i].kind, weights + L[i].w_off, L[i].cin, L[i].cout,
                                 (scale && !fc) ? scale + L[i].c_off : nullptr, shift ? shift + L[i].c_off : nullptr,
                                 fc ? MNV1_ACT_NONE : act, &ctx->net[i]);
@@ -795,7 +925,8 @@ int mnv1_plan(mnv1_ctx* ctx, int max_batch) {
   const size_t act_bytes = (size_t)max_batch * kMaxActElems * elem_size(ctx->dtype);
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&ctx->act[i], act_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_pooled, (size_t)max_batch * 1024 * 4);
+  // fp32 pooled means [n][1024]; integer contexts keep their u8 pooled vector and u8 logits in the 2 KB per image behind it
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_pooled, (size_t)max_batch * (1024 * 4 + 2048));
   for (auto& sl : ctx->slots) {
     if (e == cudaSuccess) e = cudaMalloc(&sl.d_images, (size_t)max_batch * kImgBytes);
     if (e == cudaSuccess) e = cudaMalloc(&sl.d_logits, (size_t)max_batch * MNV1_NUM_CLASSES * 4);
@@ -863,6 +994,18 @@ static cudaError_t enqueue_layers(mnv1_ctx* ctx, const uint8_t* d_img, int n, in
         cur = dst; side ^= 1;
         break;
       case MNV1_POOL:
+        if (ctx->dtype == MNV1_U8) {   // kernel.cl:116-131: integer mean, u8
+          uint8_t* pooled8 = (uint8_t*)ctx->d_pooled + (size_t)ctx->plan_batch * 4096;
+          ctx->launches++; ctx->last_kernel = "pool_u8_kernel";
+          e = mnv1::launch_pool_u8(pooled8, (const uint8_t*)cur, n, L[i].hin * L[i].hin, L[i].cout, ctx->u8_wrap, ctx->stream);
+          cur = pooled8;
+          if (last == i + 1 && e == cudaSuccess) {           // per-layer dump: as fp32 [n][1024]
+            e = mnv1::launch_u8_to_f32(ctx->d_pooled, pooled8, (long)n * L[i].cout, ctx->stream);
+            ctx->launches++;
+            cur = ctx->d_pooled;
+          }
+          break;
+        }
         if (last == i + 1) {  // pool alone (per-layer dump): fp32 means
           ctx->launches++; ctx->last_kernel = "pool_kernel";
           e = mnv1::launch_pool(ctx->dtype, ctx->d_pooled, cur, n, L[i].hin * L[i].hin, L[i].cout, true, ctx->stream);
@@ -870,6 +1013,19 @@ static cudaError_t enqueue_layers(mnv1_ctx* ctx, const uint8_t* d_img, int n, in
         }
         break;  // otherwise fused into the head below
       case MNV1_FC: {
+        if (ctx->dtype == MNV1_U8) {   // the FC launch of `pointwise` (MobileNet.c:2681-2763), then the softmax over the u8 logits
+          uint8_t* logits8 = (uint8_t*)ctx->d_pooled + (size_t)ctx->plan_batch * 4096 + (size_t)ctx->plan_batch * 1024;
+          ctx->err.clear();
+          ctx->launches++; ctx->last_kernel = "pointwise_i8_kernel";
+          e = mnv1::launch_pointwise_i8(logits8, (const uint8_t*)cur, f, n, 1024, MNV1_NUM_CLASSES, ctx->u8_wrap, ctx->stream, &ctx->err);
+          if (e == cudaSuccess) { e = mnv1::launch_u8_to_f32(d_logits, logits8, (long)n * MNV1_NUM_CLASSES, ctx->stream); ctx->launches++; }
+          if (e == cudaSuccess && (d_top1 || d_prob)) {
+            e = mnv1::launch_softmax(d_logits, n, MNV1_NUM_CLASSES, nullptr, d_top1, d_prob, ctx->stream);
+            ctx->launches++;
+          }
+          cur = d_logits;
+          break;
+        }
         int nl = 0;
         e = mnv1::launch_head(ctx->dtype, cur, n, 49, 1024, f, ctx->d_pooled, d_logits, d_top1, d_prob,
                               MNV1_NUM_CLASSES, ctx->gather, ctx->stream, &nl);
@@ -892,6 +1048,8 @@ static int check_ready(mnv1_ctx* ctx, int n) {
     int rc = mnv1_plan(ctx, n);
     if (rc) return rc;
   }
+  if (ctx->dtype == MNV1_U8 && (ctx->in_scale != 1.f || ctx->in_bias != 0.f))
+    return fail(ctx, MNV1_EUNSUPPORTED, "integer contexts read the raw u8 pixels (input transform must be 1, 0)");
   return prepare_stem(ctx, ctx->net[0]);
 }
 

@@ -39,6 +39,12 @@ struct mnv1_filter {
   float h_shift2[32] = {};  // host copy of shift2 (constant-bank epilogue of stem_rows.cu)
   float prep_scale = 0.f, prep_bias = 0.f, p0 = 0.f;
   bool prepared = false;
+  // integer contexts (MNV1_U8, int8.cu): s8 filter in the kernel's order (stem: packed [32][7] words in w_q32,
+  // depthwise [9][C], pointwise / fc [Cout][Cin]), s32 bias, right shift of the requantisation
+  int8_t* w_s8 = nullptr;
+  int* w_q32 = nullptr;
+  int* bias_i32 = nullptr;
+  int rshift = 0;
   CUtensorMap tmap_b;       // TMA descriptor of w_bf16 (pointwise, bf16 contexts)
   bool has_tmap = false;
   int tmap_bn = 0;          // N-tile the descriptor's box was built for
@@ -188,4 +194,14 @@ cudaError_t launch_nhwc_to_nchw(mnv1_dtype dt, float* out_nchw, const void* in_n
                                 int h, int w, cudaStream_t st);
 cudaError_t launch_synth_images(uint8_t* out, long first_byte, long nbytes, uint64_t seed,
                                 cudaStream_t st);
+// ---- integer contexts (int8.cu): u8 activations x s8 filters -> s32 -> u8
+cudaError_t launch_pointwise_i8(uint8_t* out, const uint8_t* in, const mnv1_filter* f, long m, int k, int cout, int wrap,
+                                cudaStream_t st, std::string* err);
+cudaError_t launch_depthwise_u8(uint8_t* out, const uint8_t* in, const mnv1_filter* f, int n, int rows, int cols, int stride,
+                                int c, int pad_lo, int wrap, cudaStream_t st);
+cudaError_t launch_stem_u8(uint8_t* out, const StemArgs& a, const mnv1_filter* f, int wrap, cudaStream_t st);
+cudaError_t launch_pool_u8(uint8_t* out, const uint8_t* in, int n, int hw, int c, int wrap, cudaStream_t st);
+// dir 0: planar host order (u8 or float values) -> NHWC u8; dir 1: NHWC u8 -> planar (u8 or float)
+cudaError_t launch_u8_layout(int dir, void* out, const void* in, bool host_is_u8, int n, int c, int hw, cudaStream_t st);
+cudaError_t launch_u8_to_f32(float* out, const uint8_t* in, long count, cudaStream_t st);
 }  // namespace mnv1

@@ -35,7 +35,10 @@ extern "C" {
 #define MNV1_ESTATE (-5)       /* call order: weights not loaded, plan missing, ...      */
 #define MNV1_EUNSUPPORTED (-6) /* shape outside what the sm_100a kernels implement       */
 
-typedef enum { MNV1_F32 = 0, MNV1_BF16 = 1 } mnv1_dtype;
+/* MNV1_U8: the reference's own integer arithmetic (kernel.cl:2-3,62,94: unsigned char maps x int filters summed
+ * in an int, `if (sum <= 0) sum = 0`, stored to unsigned char): u8 activations, s8 filters, s32 accumulation on
+ * tcgen05.mma.kind::i8 / DP4A; see mnv1_ctx_set_u8_store and the note at mnv1_filter_create. */
+typedef enum { MNV1_F32 = 0, MNV1_BF16 = 1, MNV1_U8 = 2 } mnv1_dtype;
 typedef enum { MNV1_ACT_NONE = 0, MNV1_ACT_RELU = 1, MNV1_ACT_RELU6 = 2 } mnv1_act;
 /* padding of stride-2 layers: REF = 1 px top/left (kernel.cl:20,79 `< 0` test),
  * TFSAME = Keras/TF "SAME" on even sizes (0 top/left, 1 bottom/right). Stride 1: 1 px all round. */
@@ -77,10 +80,21 @@ int mnv1_upload_u8(mnv1_ctx* ctx, mnv1_buf* buf, const uint8_t* host, size_t byt
 int mnv1_upload_planar(mnv1_ctx* ctx, mnv1_buf* buf, const float* host_nchw);
 int mnv1_download_planar(mnv1_ctx* ctx, mnv1_buf* buf, float* host_nchw);
 void* mnv1_buf_device_ptr(mnv1_buf* buf);
+/* integer contexts: planar u8 host arrays, the reference's own `unsigned char*` layout (MobileNet.c:116-143,
+ * :350 clEnqueueWriteBuffer, :395 clEnqueueReadBuffer), no fp32 detour */
+int mnv1_upload_planar_u8(mnv1_ctx* ctx, mnv1_buf* buf, const uint8_t* host_nchw);
+int mnv1_download_planar_u8(mnv1_ctx* ctx, mnv1_buf* buf, uint8_t* host_nchw);
+/* integer contexts: how an s32 result becomes the u8 that is stored.  wrap = 1: the C conversion to unsigned
+ * char, i.e. modulo 256 — literally what kernel.cl:56,90,112 do; wrap = 0 (default): saturate to [0, 255]. */
+int mnv1_ctx_set_u8_store(mnv1_ctx* ctx, int wrap);
 
 /* ---- filters: replace readSquezeNetKernel + clCreateBuffer(d_filter) (MobileNet.c:31-47,
  *      241,248).  `w` is in the reference's flat order for that kernel kind; scale/shift
  *      (per output channel, may be NULL) are a folded BatchNorm or, for MNV1_FC, the bias. -- */
+/* Integer contexts (MNV1_U8): `w` must hold integers in [-128, 127] (the int8_t filter buffers of
+ * MobileNet.c:116,248); out = store_u8(act(acc + shift[c]) >> s) with shift an integer bias and scale = 2^-s the
+ * same power of two for every channel (NULL: s = 0).  scale = shift = NULL, MNV1_ACT_RELU and the wrapping store
+ * reproduce kernel.cl bit for bit. */
 int mnv1_filter_create(mnv1_ctx* ctx, mnv1_kind kind, const float* w, int cin, int cout,
                        const float* scale, const float* shift, mnv1_act act,
                        mnv1_filter** filter);

@@ -22,7 +22,25 @@ float mnv1o_round_bf16(float x) {
   return x;
 }
 
+/* Integer modes (round_bf16 = MNV1O_STORE_U8_SAT / _WRAP): the reference's own arithmetic, exactly —
+ * `int sum` (kernel.cl:10,70,100), `if (sum <= 0) sum = 0` (:52-54,87-89,109-111), stored to `unsigned char`
+ * (:56,90,112: the C conversion, i.e. modulo 256).  Generalised by an integer bias and a right shift:
+ *   v = sum + shift[c];  ReLU;  v >>= s  (scale[c] = 2^-s);  store = v mod 256 (WRAP) or clamp(v, 0, 255) (SAT).
+ * Computed in 64-bit integers from the (exact) double accumulator. */
+static inline float epilogue_int(double acc, int c, const mnv1o_epilogue* ep) {
+  long long v = llround(acc);
+  if (ep->shift) v += llround((double)ep->shift[c]);
+  if (ep->act != MNV1O_ACT_NONE && v < 0) v = 0;
+  int s = 0;
+  if (ep->scale) while (s < 31 && ep->scale[c] != ldexpf(1.0f, -s)) ++s;
+  v = (v >= 0) ? (v >> s) : -((-v + (1LL << s) - 1) >> s); /* floor division by 2^s */
+  if (ep->round_bf16 == MNV1O_STORE_U8_WRAP) v = ((v % 256) + 256) % 256;
+  else v = v < 0 ? 0 : v > 255 ? 255 : v;
+  return (float)v;
+}
+
 static inline float epilogue(double acc, int c, const mnv1o_epilogue* ep) {
+  if (ep && ep->round_bf16 >= MNV1O_STORE_U8_SAT) return epilogue_int(acc, c, ep);
   float y = (float)acc;
   if (ep) {
     float s = ep->scale ? ep->scale[c] : 1.0f;
@@ -203,8 +221,9 @@ void mnv1o_forward(const uint8_t* images, int n, const float* weights, const flo
   long cur_elems = 0;
   for (int k = 0; k < last_layer && k < NL; ++k) {
     const mnv1o_layer* L = &g_layers[k];
+    const int int_mode = round_bf16 >= MNV1O_STORE_U8_SAT;   /* the whole chain in the reference's integers */
     mnv1o_epilogue ep = {scale ? scale + L->c_off : NULL, shift ? shift + L->c_off : NULL, act,
-                         round_bf16 & 1};
+                         int_mode ? round_bf16 : (round_bf16 & 1)};
     long out_elems = (long)n * L->cout * L->hout * L->hout;
     float* nxt = (float*)malloc((size_t)out_elems * sizeof(float));
     const float* w = weights + L->w_off;
@@ -220,11 +239,13 @@ void mnv1o_forward(const uint8_t* images, int n, const float* weights, const flo
         mnv1o_pointwise(nxt, cur, w, n, L->hin, L->hin, L->cin, L->cout, &ep);
         break;
       case 3:
-        mnv1o_pool(nxt, cur, n, L->hin, L->hin, L->hin, L->cout, 0, (round_bf16 >> 1) & 1);
+        if (int_mode) mnv1o_pool(nxt, cur, n, L->hin, L->hin, L->hin, L->cout, 1, 0);   /* kernel.cl:129 integer division */
+        else mnv1o_pool(nxt, cur, n, L->hin, L->hin, L->hin, L->cout, 0, (round_bf16 >> 1) & 1);
         break;
       case 4: { /* FC = pointwise at rows=cols=1 (MobileNet.c:2689), bias, no activation,
                    logits kept in fp32 */
         mnv1o_epilogue fe = {NULL, shift ? shift + L->c_off : NULL, MNV1O_ACT_NONE, 0};
+        if (int_mode) fe = ep;   /* the reference's FC is its `pointwise` kernel, ReLU and u8 store included (MobileNet.c:2689-2754) */
         mnv1o_pointwise(nxt, cur, w, n, 1, 1, L->cin, L->cout, &fe);
         break;
       }

@@ -41,11 +41,16 @@ enum { MNV1O_ACT_NONE = 0, MNV1O_ACT_RELU = 1, MNV1O_ACT_RELU6 = 2 };
  *   TFSAME : Keras/TF "SAME" on even sizes = 0 top/left, 1 bottom/right           */
 enum { MNV1O_PAD_REF = 0, MNV1O_PAD_TFSAME = 1 };
 
+/* values of mnv1o_epilogue.round_bf16 (the "how is the result stored" field) */
+enum { MNV1O_STORE_F32 = 0, MNV1O_STORE_BF16 = 1, MNV1O_STORE_U8_SAT = 2, MNV1O_STORE_U8_WRAP = 3 };
+
 typedef struct {
   const float* scale;   /* per output channel, NULL = 1  (folded BatchNorm)       */
   const float* shift;   /* per output channel, NULL = 0  (folded BatchNorm / bias) */
   int act;              /* MNV1O_ACT_*                                            */
-  int round_bf16;       /* 1 = round the stored result to bfloat16 (RNE)          */
+  int round_bf16;       /* MNV1O_STORE_*: 1 = round the stored result to bfloat16 (RNE);
+                           2 / 3 = the reference's integer arithmetic with a saturating / wrapping
+                           u8 store: out = store(act(sum + shift[c]) >> s), scale[c] = 2^-s        */
 } mnv1o_epilogue;
 
 /* kernel.cl:2-60.  r,g,b: [n][rows][cols] u8 planes with element stride `pix_stride`

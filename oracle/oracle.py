@@ -16,6 +16,7 @@ ORACLE_SO = os.path.join(HERE, "libmnv1_oracle.so")
 LITERAL_SO = os.path.join(HERE, "_ref", "libmnv1_literal.so")
 
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2
+STORE_F32, STORE_BF16, STORE_U8_SAT, STORE_U8_WRAP = 0, 1, 2, 3   # the `rbf16` argument below takes these too
 PAD_REF, PAD_TFSAME = 0, 1
 
 
