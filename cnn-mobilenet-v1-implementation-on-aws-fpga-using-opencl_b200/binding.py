@@ -316,6 +316,10 @@ class Context:
     # ---- logits gather of the data-parallel mode (peer stores from the head kernel)
     def gather_create(self, world: int, rank: int, rows_per_rank: int):
         self._ck(lib().mnv1_gather_create(self.h, world, rank, rows_per_rank))
+        self._gather = True
+
+    def gather_active(self) -> bool:
+        return getattr(self, "_gather", False)
 
     def gather_attach(self, peer: "Context"):
         self._ck(lib().mnv1_gather_attach(self.h, peer.h))
@@ -335,6 +339,15 @@ class Context:
 
     def gather_destroy(self):
         self._ck(lib().mnv1_gather_destroy(self.h))
+        self._gather = False
+
+    def h2d_probe(self, nbytes: int, reps: int = 20) -> float:
+        g = C.c_float()
+        self._ck(lib().mnv1_h2d_probe(self.h, C.c_size_t(nbytes), reps, C.byref(g)))
+        return g.value
+
+    def forward_prefix_device(self, d_images: int, n: int, last_layer: int):
+        self._ck(lib().mnv1_forward_prefix_device(self.h, C.c_void_p(d_images), n, last_layer))
 
     def profile_prefixes(self, d_images: int, n: int, iters: int = 21) -> np.ndarray:
         """cum_ms[k-1]: median replay time of the graph of layers 1..k (-1 where no launch ends at layer k)."""

@@ -30,7 +30,7 @@ const mnv1::Switches& mnv1::switches() {
     sw.no_pair = getenv("MNV1_NO_PAIR") != nullptr;
     sw.no_cw = getenv("MNV1_NO_CW") != nullptr;
     sw.no_stem_rows = getenv("MNV1_NO_STEM_ROWS") != nullptr;
-    sw.no_fused_head = getenv("MNV1_NO_FUSED_HEAD") != nullptr;
+    sw.fused_head = getenv("MNV1_FUSED_HEAD") != nullptr;   // one cluster kernel for pool+FC+softmax: correct, still slower than the three launches
     sw.no_fused_pair = getenv("MNV1_NO_FUSED_PAIR") != nullptr;
     sw.rb_mask = getenv("MNV1_RB_MASK") ? strtol(getenv("MNV1_RB_MASK"), nullptr, 0) : ~0L;
   });
@@ -1252,6 +1252,16 @@ int mnv1_forward_upto(mnv1_ctx* ctx, const uint8_t* images, int n, int last_laye
   return mnv1_download_planar(ctx, &view, host_nchw);
 }
 
+// layers 1..last_layer on device-resident images, eagerly, no copies (kernel bring-up, ncu, bench.py's kernel names)
+int mnv1_forward_prefix_device(mnv1_ctx* ctx, const void* d_images, int n, int last_layer) {
+  GUARD(ctx);
+  int rc = check_ready(ctx, n);
+  if (rc) return rc;
+  if (!d_images || last_layer < 1 || last_layer > MNV1_NUM_LAYERS) return fail(ctx, MNV1_EINVAL, "forward_prefix_device: bad arguments");
+  CK(ctx, enqueue_layers(ctx, (const uint8_t*)d_images, n, last_layer, ctx->d_logits, ctx->d_top1, ctx->d_prob, nullptr, nullptr));
+  return MNV1_OK;
+}
+
 int mnv1_profile_layers(mnv1_ctx* ctx, const void* d_images, int n, int iters, float* times_ms) {
   GUARD(ctx);
   int rc = check_ready(ctx, n);
@@ -1312,7 +1322,7 @@ int mnv1_gather_create(mnv1_ctx* ctx, int world, int rank, int rows_per_rank) {
   GUARD(ctx);
   if (!ctx || world < 1 || world > 8 || rank < 0 || rank >= world || rows_per_rank <= 0)
     return fail(ctx, MNV1_EINVAL, "gather_create: need 1 <= world <= 8, 0 <= rank < world, rows_per_rank > 0");
-  if (ctx->dtype != MNV1_BF16) return fail(ctx, MNV1_EUNSUPPORTED, "gather: bf16 contexts only (the cluster head kernel does the stores)");
+  if (ctx->dtype == MNV1_U8) return fail(ctx, MNV1_EUNSUPPORTED, "gather: fp32 / bf16 contexts (the softmax kernel does the stores)");
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   gather_release(ctx);
   cudaError_t e = cudaMalloc(&ctx->g_block, gather_bytes(world * rows_per_rank));
@@ -1396,15 +1406,14 @@ int mnv1_profile_prefixes(mnv1_ctx* ctx, const void* d_images, int n, int iters,
   int fused[MNV1_NUM_LAYERS];
   if ((rc = mnv1_fused_layers(ctx, fused)) != MNV1_OK) return rc;
   const LayerDef* L = layer_defs();
-  std::vector<cudaEvent_t> evs(iters + 1);
-  for (auto& e : evs) CK(ctx, cudaEventCreate(&e));
-  std::vector<float> t(iters);
-  cudaError_t e = cudaSuccess;
   const long launches_before = ctx->launches;
+  std::vector<int> cuts;
+  std::vector<cudaGraphExec_t> execs;
+  cudaError_t e = cudaSuccess;
   for (int k = 1; k <= MNV1_NUM_LAYERS && e == cudaSuccess; ++k) {
     cum_ms[k - 1] = -1.f;
     if (fused[k - 1]) continue;                                               // ends inside a fused dw+pw launch
-    if (L[k - 1].kind == MNV1_POOL && ctx->dtype == MNV1_BF16) continue;       // pooled inside the head kernel
+    if (L[k - 1].kind == MNV1_POOL && ctx->dtype == MNV1_BF16) continue;       // one "head" row for pool + FC + softmax
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
@@ -1415,23 +1424,70 @@ int mnv1_profile_prefixes(mnv1_ctx* ctx, const void* d_images, int n, int iters,
     if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
     if (graph) cudaGraphDestroy(graph);
     if (e != cudaSuccess) break;
-    for (int w = 0; w < 2 && e == cudaSuccess; ++w) e = cudaGraphLaunch(exec, ctx->stream);   // warm-up
-    for (int it = 0; it < iters && e == cudaSuccess; ++it) {
-      cudaEventRecord(evs[it], ctx->stream);
-      e = cudaGraphLaunch(exec, ctx->stream);
-    }
-    cudaEventRecord(evs[iters], ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e == cudaSuccess) {
-      for (int it = 0; it < iters; ++it) cudaEventElapsedTime(&t[it], evs[it], evs[it + 1]);
-      std::sort(t.begin(), t.end());
-      cum_ms[k - 1] = t[iters / 2];
-    }
-    cudaGraphExecDestroy(exec);
+    cuts.push_back(k);
+    execs.push_back(exec);
   }
+  const int nc = (int)cuts.size();
+  std::vector<cudaEvent_t> evs(2 * (size_t)nc);
+  for (auto& ev : evs) if (e == cudaSuccess) e = cudaEventCreate(&ev);
+  // Every repetition replays all the prefixes back to back, so that the two times a difference is made of are
+  // taken milliseconds apart, under the same clocks; the per-launch time is the median over the repetitions
+  // of that difference.
+  std::vector<std::vector<float>> diff(nc, std::vector<float>(iters));
+  for (int it = -2; it < iters && e == cudaSuccess; ++it) {                 // two warm-up rounds
+    for (int j = 0; j < nc && e == cudaSuccess; ++j) {
+      cudaEventRecord(evs[2 * j], ctx->stream);
+      e = cudaGraphLaunch(execs[j], ctx->stream);
+      cudaEventRecord(evs[2 * j + 1], ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess || it < 0) continue;
+    float prev = 0.f;
+    for (int j = 0; j < nc; ++j) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, evs[2 * j], evs[2 * j + 1]);
+      diff[j][it] = t - prev;
+      prev = t;
+    }
+  }
+  if (e == cudaSuccess) {
+    float cum = 0.f;
+    for (int j = 0; j < nc; ++j) {
+      std::sort(diff[j].begin(), diff[j].end());
+      cum += diff[j][iters / 2];
+      cum_ms[cuts[j] - 1] = cum;
+    }
+  }
+  for (auto ex : execs) cudaGraphExecDestroy(ex);
+  for (auto& ev : evs) if (ev) cudaEventDestroy(ev);
   ctx->launches = launches_before;
-  for (auto& ev : evs) cudaEventDestroy(ev);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "profile_prefixes");
+  return MNV1_OK;
+}
+
+// What a plain pinned cudaMemcpyAsync reaches on this box: `reps` back-to-back host-to-device copies of
+// `bytes` on the context's copy stream, CUDA events.  The ceiling of mnv1_forward's upload.
+int mnv1_h2d_probe(mnv1_ctx* ctx, size_t bytes, int reps, float* gbytes_per_s) {
+  GUARD(ctx);
+  if (!ctx || !bytes || reps <= 0 || !gbytes_per_s) return fail(ctx, MNV1_EINVAL, "h2d_probe: bad arguments");
+  void *h = nullptr, *d = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t e = cudaMallocHost(&h, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d, bytes);
+  if (e == cudaSuccess) { memset(h, 1, bytes); e = cudaEventCreate(&e0); }
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+  if (e == cudaSuccess) e = cudaEventRecord(e0, ctx->copy_stream);
+  for (int i = 0; i < reps && e == cudaSuccess; ++i) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+  if (e == cudaSuccess) e = cudaEventRecord(e1, ctx->copy_stream);
+  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(d); cudaFreeHost(h);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "h2d_probe");
+  *gbytes_per_s = (float)((double)bytes * reps / (ms * 1e-3) / 1e9);
   return MNV1_OK;
 }
 

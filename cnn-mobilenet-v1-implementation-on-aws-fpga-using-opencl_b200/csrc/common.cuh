@@ -98,7 +98,7 @@ namespace mnv1 {
 bool pdl_enabled();
 // Environment switches (fall back to the previous kernel of a layer; timing experiments): read ONCE per
 // process, by the first mnv1_ctx_create — never from a launch path.
-struct Switches { bool no_pdl, no_pair, no_cw, no_stem_rows, no_fused_head, no_fused_pair; long rb_mask; };
+struct Switches { bool no_pdl, no_pair, no_cw, no_stem_rows, fused_head, no_fused_pair; long rb_mask; };
 const Switches& switches();
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remembered per (function,
 // current device), thread-safe, so that a second context on another GPU of the same process opts in too.
@@ -186,8 +186,9 @@ struct HeadGather {
 cudaError_t launch_head(mnv1_dtype dt, const void* in, int n, int hw, int c, const mnv1_filter* fc,
                         float* pooled_scratch, float* logits, int* top1, float* top1_prob,
                         int classes, const HeadGather& gather, cudaStream_t st, int* launches);
+struct HeadGather;
 cudaError_t launch_softmax(const float* logits, int n, int classes, float* prob, int* top1,
-                           float* top1_prob, cudaStream_t st);
+                           float* top1_prob, cudaStream_t st, const HeadGather* gather = nullptr);
 cudaError_t launch_nchw_to_nhwc(mnv1_dtype dt, void* out_nhwc, const float* in_nchw, int n, int c,
                                 int h, int w, cudaStream_t st);
 cudaError_t launch_nhwc_to_nchw(mnv1_dtype dt, float* out_nchw, const void* in_nhwc, int n, int c,

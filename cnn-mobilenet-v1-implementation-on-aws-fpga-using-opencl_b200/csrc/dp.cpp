@@ -138,7 +138,7 @@ int mnv1_dp_create(const int* devices, int n_devices, mnv1_dtype dtype, int max_
     if (rc) return bail(rc, std::string("dp_create: device ") + std::to_string(devices[r]) + ": " + mnv1_last_error(nullptr));
     dp->workers.emplace_back(new Worker);
   }
-  if (dtype == MNV1_BF16) {   // the gather lives in the bf16 head kernel; fp32 groups only shard
+  if (dtype != MNV1_U8) {   // the gather stores live in the softmax kernel of the fp32 / bf16 head
     for (int r = 0; r < n_devices; ++r) {
       int rc = mnv1_gather_create(dp->ctx[r], n_devices, r, max_batch_per_gpu);
       if (rc) return bail(rc, std::string("dp_create: ") + mnv1_last_error(dp->ctx[r]));

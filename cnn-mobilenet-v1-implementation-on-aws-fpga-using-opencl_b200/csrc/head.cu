@@ -270,7 +270,7 @@ cudaError_t launch_fc(float* out, const float* pooled, const float* w_f32, const
 constexpr int SM_THREADS = 128, SM_PER = 8;
 __global__ void __launch_bounds__(SM_THREADS) softmax_kernel(const float* __restrict__ logits, int n, int classes,
                                                              float* __restrict__ prob, int* __restrict__ top1,
-                                                             float* __restrict__ top1_prob) {
+                                                             float* __restrict__ top1_prob, const HeadGather g) {
   __shared__ float s_mx[4], s_sum[4];
   __shared__ int s_arg[4];
   pdl_trigger();
@@ -282,6 +282,13 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_kernel(const float* __rest
   for (int i = 0; i < SM_PER; ++i) {
     const int k = threadIdx.x + i * SM_THREADS;
     v[i] = k < classes ? z[k] : -INFINITY;
+  }
+  // logits gather of the data-parallel mode: this image's row goes straight into the gather block of every
+  // rank (peer-mapped pointers, NVLink) — fire-and-forget stores, no collective kernel in the step
+  for (int d = 0; d < g.n_dst; ++d) {
+    float* dst = g.logits[d] + (g.row0 + img) * (long)classes;
+#pragma unroll
+    for (int i = 0; i < SM_PER; ++i) { const int k = threadIdx.x + i * SM_THREADS; if (k < classes) dst[k] = v[i]; }
   }
   float mx = -INFINITY;
   int arg = 0x7fffffff;
@@ -319,6 +326,10 @@ __global__ void __launch_bounds__(SM_THREADS) softmax_kernel(const float* __rest
   if (threadIdx.x == 0) {
     if (top1) top1[img] = arg;
     if (top1_prob) top1_prob[img] = inv;
+    for (int d = 0; d < g.n_dst; ++d) {
+      if (g.top1[d]) g.top1[d][g.row0 + img] = arg;
+      if (g.prob[d]) g.prob[d][g.row0 + img] = inv;
+    }
   }
 }
 
@@ -355,10 +366,12 @@ __global__ void __launch_bounds__(128) softmax_warp_kernel(const float* __restri
 }
 
 cudaError_t launch_softmax(const float* logits, int n, int classes, float* prob, int* top1, float* top1_prob,
-                           cudaStream_t st) {
+                           cudaStream_t st, const HeadGather* gather) {
   if (n <= 0) return cudaSuccess;
+  const HeadGather g = gather ? *gather : HeadGather{};
   if (classes <= SM_THREADS * SM_PER)
-    return launch_pdl(softmax_kernel, dim3((unsigned)n), dim3(SM_THREADS), 0, st, logits, n, classes, prob, top1, top1_prob);
+    return launch_pdl(softmax_kernel, dim3((unsigned)n), dim3(SM_THREADS), 0, st, logits, n, classes, prob, top1, top1_prob, g);
+  if (g.n_dst) return cudaErrorNotSupported;
   else softmax_warp_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(logits, n, classes, prob, top1, top1_prob);
   return cudaGetLastError();
 }
@@ -542,7 +555,7 @@ head_fused_kernel(const bf16* __restrict__ in, const bf16* __restrict__ w, const
 cudaError_t launch_head_fused(const bf16* in, int n, int hw, int c, const mnv1_filter* fc, float* pooled_scratch,
                               float* logits, int* top1, float* top1_prob, int classes, const HeadGather& g,
                               cudaStream_t st) {
-  if (c != 1024 || classes > HF_CL * HF_CLS || !fc->w_bf16 || switches().no_fused_head) return cudaErrorNotSupported;
+  if (c != 1024 || classes > HF_CL * HF_CLS || !fc->w_bf16 || !switches().fused_head) return cudaErrorNotSupported;
   if (n <= 0) return cudaSuccess;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(((n + HF_IMGS - 1) / HF_IMGS) * HF_CL));
@@ -564,7 +577,6 @@ cudaError_t launch_head(mnv1_dtype dt, const void* in, int n, int hw, int c, con
     cudaError_t fe = launch_head_fused((const bf16*)in, n, hw, c, fc, pooled_scratch, logits, top1, top1_prob, classes, g, st);
     if (fe != cudaErrorNotSupported) { if (launches) *launches = 1; return fe; }
   }
-  if (g.n_dst) return cudaErrorNotSupported;   // the peer gather lives in the fused kernel only
   cudaError_t e = launch_pool(dt, pooled_scratch, in, n, hw, c, /*out_f32=*/true, st);
   if (e != cudaSuccess) return e;
   e = launch_fc(logits, pooled_scratch, fc->w_f32, dt == MNV1_BF16 ? fc->w_bf16 : nullptr, fc->shift, n, c, classes, st);
@@ -574,8 +586,8 @@ cudaError_t launch_head(mnv1_dtype dt, const void* in, int n, int hw, int c, con
   }
   if (e != cudaSuccess) return e;
   if (launches) *launches = 2;
-  if (top1 || top1_prob) {
-    e = launch_softmax(logits, n, classes, nullptr, top1, top1_prob, st);
+  if (top1 || top1_prob || g.n_dst) {
+    e = launch_softmax(logits, n, classes, nullptr, top1, top1_prob, st, &g);
     if (launches) *launches = 3;
   }
   return e;

@@ -173,6 +173,8 @@ int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images_u8, int n, void* d_l
  * (the per-layer parity dump; configs "first 5 layers" / "first 13 layers") */
 int mnv1_forward_upto(mnv1_ctx* ctx, const uint8_t* images, int n, int last_layer,
                       float* host_nchw);
+/* layers 1..last_layer on device-resident images, eagerly on the context stream, nothing copied */
+int mnv1_forward_prefix_device(mnv1_ctx* ctx, const void* d_images_u8, int n, int last_layer);
 /* per-layer device time (ms) of the last mnv1_profile_layers run; times[29] */
 int mnv1_profile_layers(mnv1_ctx* ctx, const void* d_images_u8, int n, int iters, float* times_ms);
 /* per-launch device time inside the replayed CUDA graph: cum_ms[k-1] = median time of the graph of layers
@@ -180,6 +182,9 @@ int mnv1_profile_layers(mnv1_ctx* ctx, const void* d_images_u8, int n, int iters
  * fused with its pointwise, the pool inside the head kernel).  Consecutive differences are per-launch times
  * that add up to the whole step; what MobileNet.c:303-305,315 printed per layer, without the host round trip. */
 int mnv1_profile_prefixes(mnv1_ctx* ctx, const void* d_images_u8, int n, int iters, float* cum_ms29);
+/* GB/s of `reps` back-to-back pinned cudaMemcpyAsync host-to-device copies of `bytes` (the ceiling of the
+ * upload inside mnv1_forward; replaces nothing in the reference, whose clEnqueueWriteBuffer is blocking) */
+int mnv1_h2d_probe(mnv1_ctx* ctx, size_t bytes, int reps, float* gbytes_per_s);
 /* fill d_images (u8 [n][224][224][3]) with the synthetic stream of SURVEY §8(d): images
  * first..first+n-1 of seed `seed`, generated on the device */
 int mnv1_synth_images_device(mnv1_ctx* ctx, void* d_images_u8, int n, long first, uint64_t seed);

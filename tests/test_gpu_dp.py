@@ -125,20 +125,21 @@ def test_gather_between_two_plain_contexts(mn, synth_net):
 
 
 def test_fused_head_matches_three_kernel_head(mn, synth_net, monkeypatch):
-    """head_fused_kernel (cluster of 8 CTAs: pool -> FC -> softmax) against the pool / fc_mma / softmax launches
-    it replaces: same arithmetic in the same order, so the logits and top-1 are bit-identical."""
+    """head_fused_kernel (cluster of 8 CTAs: pool -> FC -> softmax; opt-in with MNV1_FUSED_HEAD=1 until it beats the
+    three launches) against the pool / fc_mma / softmax launches: same arithmetic in the same order, so the logits
+    and top-1 are bit-identical."""
     import subprocess, sys, os, json
     from mnv1_b200 import synth
     img = synth.images(37)
     got_l, got_t, got_p = _single(mn, synth_net, img)
-    # the switch is read once per process: run the three-kernel head in a child
+    # the switch is read once per process: run the cluster head in a child
     code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import mnv1_b200; from mnv1_b200 import binding as mn, synth;"
             "w = synth.weights(); sc, sh = synth.batchnorm(); c = mn.Context(0, mn.BF16); c.set_pad_mode(1);"
             "c.set_input_transform(1/127.5, -1.0); c.set_weights(w, sc, sh, mn.ACT_RELU6);"
             "l, t, p = c.forward(synth.images(37)); np.save(sys.argv[1], l); print(json.dumps(t.tolist()))") % \
         os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     path = "/tmp/mnv1_head3.npy"
-    env = dict(os.environ, MNV1_NO_FUSED_HEAD="1")
+    env = dict(os.environ, MNV1_FUSED_HEAD="1")
     r = subprocess.run([sys.executable, "-c", code, path], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     want_l = np.load(path)

@@ -148,22 +148,33 @@ def test_compare_logs_parses_reference_format():
     assert cl.compare("", "garbage")["rows"] == [] and cl.parse("nothing")[1] is None
 
 
-def test_bench_merges_fused_rows():
-    """a fused depthwise->pointwise launch is ONE roofline row: dw input + pw output + both filters"""
+def test_bench_launch_rows_from_graph_prefixes():
+    """bench.launch_rows: one row per launch from the cumulative prefix times (-1 = no launch ends at that layer);
+    a fused depthwise->pointwise launch is ONE row (dw input + pw output + both filters), the rows add up to the
+    last prefix time, and kernel_rooflines groups them per distinct kernel."""
     bench = _load_tool("bench")
     from mnv1_b200.layers import LAYERS
     peaks = {"hbm_gbs": 6543.1, "bf16_tflops": 1395.8}
-    times = [0.1] * 29
-    plain = bench.layer_roofline(LAYERS, times, 256, peaks)
-    fused = [0] * 29
-    fused[1] = 1            # layer 2 (dw) runs fused with layer 3 (pw)
-    merged = bench.layer_roofline(LAYERS, times, 256, peaks, fused)
-    assert len(plain) == 29 and len(merged) == 28
+    cum = [0.1 * (k + 1) for k in range(29)]
+    names = ["k%d" % (k % 3) for k in range(29)]
+    plain = bench.launch_rows(LAYERS, cum, names, 256, peaks)
+    assert len(plain) == 29 and abs(sum(r["us"] for r in plain) - cum[28] * 1e3) < 1e-6
+    fused = list(cum)
+    fused[1] = -1.0          # layer 2 (dw) runs fused with layer 3 (pw)
+    fused[27] = -1.0         # the pool runs inside the head launch
+    merged = bench.launch_rows(LAYERS, fused, names, 256, peaks)
+    assert len(merged) == 27 and abs(sum(r["us"] for r in merged) - cum[28] * 1e3) < 1e-6
     row = merged[1]
-    assert row["kind"] == "dw+pw" and row["layer"] == "2+3" and abs(row["us"] - 200.0) < 1e-6
+    assert row["kind"] == "dw+pw" and row["layer"] == "2+3" and abs(row["us"] - 200.0) < 1e-6 and row["kernel"] == "k2"
     want = (LAYERS[1].in_elems * 2 + LAYERS[2].out_elems * 2) * 256 + LAYERS[1].w_cnt * 4 + LAYERS[2].w_cnt * 2
     assert row["bytes"] == want and row["bytes"] < plain[1]["bytes"] + plain[2]["bytes"]
     assert abs(row["flops"] - (plain[1]["flops"] + plain[2]["flops"])) < 1.0
+    assert merged[-1]["layer"] == "28+29" and merged[-1]["kind"] == "pool+fc"
+    ks = bench.kernel_rooflines(merged, cum[28] * 1e3, peaks)
+    assert sorted(k["kernel"] for k in ks) == ["k0", "k1", "k2"]
+    assert sum(k["launches_per_step"] for k in ks) == 27 and abs(sum(k["share_of_step"] for k in ks) - 1.0) < 0.01
+    for k in ks:
+        assert k["unit"] == ("TFLOP/s" if k["bound"] == "tensor" else "GB/s") and 0 < k["frac"]
 
 
 def test_dp_shard_matches_python_sharding():

@@ -1,0 +1,8 @@
+#!/bin/bash
+# usage: tools/gpu_retry.sh <logfile> <gpurun args...>   — retries while the pod answers "busy" (exit 3 / transient)
+log=$1; shift
+for i in $(seq 1 40); do
+  gpurun "$@" > "$log" 2>&1
+  if ! grep -q "status=transient" "$log"; then exit 0; fi
+  sleep 45
+done
