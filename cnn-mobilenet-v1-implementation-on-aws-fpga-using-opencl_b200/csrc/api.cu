@@ -683,6 +683,20 @@ static cudaError_t run_pointwise(mnv1_ctx* ctx, void* out, const void* in, const
 }
 
 // ---------------------------------------------------------------- the four kernels
+// depthwise -> pointwise as one kernel: the CTA-pair kernel with a streamed filter for the 512-channel blocks, the
+// resident-filter kernel for the blocks whose filter fits in shared memory; cudaErrorNotSupported = no fused variant
+static cudaError_t run_fused_block(mnv1_ctx* ctx, void* out, const void* in, const mnv1_filter* dw, const mnv1_filter* pw, int n,
+                                   int rows, int cols, int stride) {
+  ctx->err.clear();
+  cudaError_t e = mnv1::launch_fused_pair((bf16*)out, (const bf16*)in, dw, pw, n, rows, cols, stride, pad_lo_for(ctx, stride),
+                                          ctx->num_sms, ctx->stream, &ctx->err);
+  if (e != cudaErrorNotSupported) { ctx->launches++; ctx->last_kernel = "fused_pair_kernel"; return e; }
+  e = mnv1::launch_fused_dw_pw((bf16*)out, (const bf16*)in, dw, pw, n, rows, cols, stride, pad_lo_for(ctx, stride), ctx->num_sms,
+                               ctx->stream, &ctx->err);
+  if (e != cudaErrorNotSupported) { ctx->launches++; ctx->last_kernel = "fused_dw_pw_kernel"; }
+  return e;
+}
+
 static int check_fmap(mnv1_ctx* ctx, const mnv1_buf* b, int c, int h, int w, const char* what) {
   if (!b || b->is_u8 || b->c != c || b->h != h || b->w != w)
     return fail(ctx, MNV1_EINVAL, std::string(what) + ": buffer shape does not match the kernel arguments");
@@ -973,13 +987,9 @@ static cudaError_t enqueue_layers(mnv1_ctx* ctx, const uint8_t* d_img, int n, in
         // depthwise + the pointwise that follows as one kernel where a fused variant exists: the
         // depthwise map then never leaves the SM
         if (ctx->use_fused && ctx->dtype == MNV1_BF16 && i + 1 < last && L[i + 1].kind == MNV1_POINTWISE) {
-          ctx->err.clear();
-          cudaError_t fe = mnv1::launch_fused_dw_pw((bf16*)dst, (const bf16*)cur, f, ctx->net[i + 1], n, L[i].hin, L[i].hin,
-                                                    L[i].stride, pad_lo_for(ctx, L[i].stride), ctx->num_sms, ctx->stream,
-                                                    &ctx->err);
+          cudaError_t fe = run_fused_block(ctx, dst, cur, f, ctx->net[i + 1], n, L[i].hin, L[i].hin, L[i].stride);
           if (fe != cudaErrorNotSupported) {
             e = fe;
-            ctx->launches++; ctx->last_kernel = "fused_dw_pw_kernel";
             cur = dst; side ^= 1;
             ++i;  // the pointwise layer is done too
             if (evs) cudaEventRecord(evs[i], ctx->stream);
@@ -1116,11 +1126,8 @@ int mnv1_dw_pw_block(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv
   if (rc) return rc;
   if (in->n != out->n) return fail(ctx, MNV1_EINVAL, "dw_pw_block: batch mismatch");
   TimedLaunch tl(ctx);
-  ctx->err.clear();
-  cudaError_t e = mnv1::launch_fused_dw_pw((bf16*)out->d, (const bf16*)in->d, dw, pw, in->n, rows, cols, stride,
-                                           pad_lo_for(ctx, stride), ctx->num_sms, ctx->stream, &ctx->err);
+  cudaError_t e = run_fused_block(ctx, out->d, in->d, dw, pw, in->n, rows, cols, stride);
   if (e == cudaErrorNotSupported) return fail(ctx, MNV1_EUNSUPPORTED, "dw_pw_block: no fused variant for this shape");
-  ctx->launches++; ctx->last_kernel = "fused_dw_pw_kernel";
   if (e != cudaSuccess) return fail_cuda(ctx, e, "dw_pw_block");
   return MNV1_OK;
 }
@@ -1135,7 +1142,8 @@ int mnv1_fused_layers(mnv1_ctx* ctx, int* fused) {
     fused[i] = 0;
     if (ctx->use_fused && ctx->dtype == MNV1_BF16 && L[i].kind == MNV1_DEPTHWISE && i + 1 < MNV1_NUM_LAYERS &&
         L[i + 1].kind == MNV1_POINTWISE)
-      fused[i] = mnv1::fused_dw_pw_supported(ctx->net[i], ctx->net[i + 1], L[i].hin, L[i].hin, L[i].stride) ? 1 : 0;
+      fused[i] = (mnv1::fused_pair_supported(ctx->net[i], ctx->net[i + 1], L[i].hin, L[i].hin, L[i].stride) ||
+                  mnv1::fused_dw_pw_supported(ctx->net[i], ctx->net[i + 1], L[i].hin, L[i].hin, L[i].stride)) ? 1 : 0;
   }
   return MNV1_OK;
 }

@@ -170,6 +170,10 @@ cudaError_t launch_fused_dw_pw(bf16* out, const bf16* in, const mnv1_filter* dw,
                                int rows, int cols, int stride, int pad_lo, int num_sms, cudaStream_t st,
                                std::string* err);
 bool fused_dw_pw_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride);
+// fused depthwise -> pointwise on CTA pairs with a streamed filter (the 512-channel 14x14 blocks, fused_pair.cu)
+cudaError_t launch_fused_pair(bf16* out, const bf16* in, const mnv1_filter* dw, const mnv1_filter* pw, int n, int rows, int cols,
+                              int stride, int pad_lo, int num_sms, cudaStream_t st, std::string* err);
+bool fused_pair_supported(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride);
 cudaError_t launch_pool(mnv1_dtype dt, void* out, const void* in, int n, int hw, int c, bool out_f32,
                         cudaStream_t st);
 // Logits gather without a collective kernel: the head kernel also stores every image's logits / top-1 /

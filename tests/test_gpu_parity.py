@@ -403,7 +403,10 @@ def test_pipelined_forward_matches_blocking(mn, synth_net, depth):
 @pytest.mark.parametrize("c,cout,h,stride,pad,n", [
     # resident-filter kernel (fused_rb.cu): the five blocks of layers 2-11, both padding conventions
     (32, 64, 112, 1, 0, 2), (64, 128, 112, 2, 1, 2), (64, 128, 112, 2, 0, 1), (128, 128, 56, 1, 0, 3),
-    (128, 256, 56, 2, 1, 3), (128, 256, 56, 2, 0, 2), (256, 256, 28, 1, 0, 5), (256, 256, 28, 1, 0, 40)])
+    (128, 256, 56, 2, 1, 3), (128, 256, 56, 2, 0, 2), (256, 256, 28, 1, 0, 5), (256, 256, 28, 1, 0, 40),
+    # CTA-pair kernel with a streamed filter (fused_pair.cu): the 512-channel 14x14 blocks, layers 14-23; one image, fewer
+    # images than clusters, several rounds per cluster with a ragged last round, the benched batch
+    (512, 512, 14, 1, 0, 1), (512, 512, 14, 1, 1, 9), (512, 512, 14, 1, 0, 100), (512, 512, 14, 1, 0, 256)])
 def test_fused_dw_pw_block(mn, oracle_mod, c, cout, h, stride, pad, n):
     """depthwise->pointwise fused kernels vs the oracle chain at bf16 storage precision, and vs the
     two separate CUDA kernels (same arithmetic in the same order: bit-identical)."""
@@ -421,9 +424,9 @@ def test_fused_dw_pw_block(mn, oracle_mod, c, cout, h, stride, pad, n):
     xin = ctx.upload_planar(x)
     out = ctx.malloc(n, cout, ho, ho)
     ctx.dw_pw_block(out, xin, fd, fp, h, h, stride)
-    assert ctx.last_kernel_name == "fused_dw_pw_kernel"
+    assert ctx.last_kernel_name == ("fused_pair_kernel" if c == 512 else "fused_dw_pw_kernel")
     got = ctx.download_planar(out)
-    if n * h * h * c <= 8 << 20:   # the oracle chain on the small cases
+    if n * h * h * c <= 8 << 20 or c == 512:   # the oracle chain on the small cases (and every CTA-pair case)
         mid = oracle_mod.depthwise(x, wd, stride, pad_mode=pad, scale=sd, shift=td, act=oracle_mod.ACT_RELU6, rbf16=True)
         want = oracle_mod.pointwise(mid, wp, cout, scale=sp, shift=tp, act=oracle_mod.ACT_RELU6, rbf16=True)
         err = np.abs(got - want) / np.maximum(1.0, np.abs(want))
@@ -442,22 +445,23 @@ def test_fused_dw_pw_block(mn, oracle_mod, c, cout, h, stride, pad, n):
 def test_fused_block_unsupported_shape(mn):
     """blocks whose filter does not fit in shared memory report MNV1_EUNSUPPORTED and launch nothing"""
     ctx = mn.Context(0, mn.BF16)
-    c = 512
+    c = 1024
     fd = ctx.filter(mn.DEPTHWISE, np.ones((c, 3, 3), np.float32), c, c, None, None, mn.ACT_RELU6)
     fp = ctx.filter(mn.POINTWISE, np.ones((c, c), np.float32), c, c, None, None, mn.ACT_RELU6)
-    x = ctx.malloc(1, c, 14, 14)
-    out = ctx.malloc(1, c, 14, 14)
+    x = ctx.malloc(1, c, 7, 7)
+    out = ctx.malloc(1, c, 7, 7)
     with pytest.raises(mn.Mnv1Error) as e:
-        ctx.dw_pw_block(out, x, fd, fp, 14, 14, 1)
+        ctx.dw_pw_block(out, x, fd, fp, 7, 7, 1)
     assert e.value.code == -6   # MNV1_EUNSUPPORTED
     ctx.close()
 
 
 def test_fused_layers_report(mn, synth_net):
-    """mnv1_fused_layers: a bf16 context fuses layers 2-11 pairwise inside mnv1_forward, an fp32 context nothing"""
+    """mnv1_fused_layers: a bf16 context fuses layers 2-11 (resident filter) and 14-23 (CTA pairs, streamed filter)
+    pairwise inside mnv1_forward, an fp32 context nothing"""
     c = _net_ctx(mn, mn.BF16, synth_net)
     f = c.fused_layers()
-    assert [i + 1 for i in range(29) if f[i]] == [2, 4, 6, 8, 10]
+    assert [i + 1 for i in range(29) if f[i]] == [2, 4, 6, 8, 10, 14, 16, 18, 20, 22]
     c.use_fused_blocks(False)
     assert not c.fused_layers().any()
     c.close()
