@@ -31,7 +31,8 @@ const mnv1::Switches& mnv1::switches() {
     sw.no_cw = getenv("MNV1_NO_CW") != nullptr;
     sw.no_stem_rows = getenv("MNV1_NO_STEM_ROWS") != nullptr;
     sw.fused_head = getenv("MNV1_FUSED_HEAD") != nullptr;   // one cluster kernel for pool+FC+softmax: correct, still slower than the three launches
-    sw.no_fused_pair = getenv("MNV1_NO_FUSED_PAIR") != nullptr;
+    sw.fused_pair = getenv("MNV1_FUSED_PAIR") != nullptr;   // layers 14-23 as CTA-pair fused blocks inside mnv1_forward*: correct, but
+                                                             // stencil-bound at 67 us per block against 45 us for the two kernels
     sw.rb_mask = getenv("MNV1_RB_MASK") ? strtol(getenv("MNV1_RB_MASK"), nullptr, 0) : ~0L;
   });
   return sw;
@@ -686,10 +687,12 @@ static cudaError_t run_pointwise(mnv1_ctx* ctx, void* out, const void* in, const
 // depthwise -> pointwise as one kernel: the CTA-pair kernel with a streamed filter for the 512-channel blocks, the
 // resident-filter kernel for the blocks whose filter fits in shared memory; cudaErrorNotSupported = no fused variant
 static cudaError_t run_fused_block(mnv1_ctx* ctx, void* out, const void* in, const mnv1_filter* dw, const mnv1_filter* pw, int n,
-                                   int rows, int cols, int stride) {
+                                   int rows, int cols, int stride, bool allow_pair) {
   ctx->err.clear();
-  cudaError_t e = mnv1::launch_fused_pair((bf16*)out, (const bf16*)in, dw, pw, n, rows, cols, stride, pad_lo_for(ctx, stride),
-                                          ctx->num_sms, ctx->stream, &ctx->err);
+  cudaError_t e = cudaErrorNotSupported;
+  if (allow_pair)
+    e = mnv1::launch_fused_pair((bf16*)out, (const bf16*)in, dw, pw, n, rows, cols, stride, pad_lo_for(ctx, stride), ctx->num_sms,
+                                ctx->stream, &ctx->err);
   if (e != cudaErrorNotSupported) { ctx->launches++; ctx->last_kernel = "fused_pair_kernel"; return e; }
   e = mnv1::launch_fused_dw_pw((bf16*)out, (const bf16*)in, dw, pw, n, rows, cols, stride, pad_lo_for(ctx, stride), ctx->num_sms,
                                ctx->stream, &ctx->err);
@@ -987,7 +990,7 @@ static cudaError_t enqueue_layers(mnv1_ctx* ctx, const uint8_t* d_img, int n, in
         // depthwise + the pointwise that follows as one kernel where a fused variant exists: the
         // depthwise map then never leaves the SM
         if (ctx->use_fused && ctx->dtype == MNV1_BF16 && i + 1 < last && L[i + 1].kind == MNV1_POINTWISE) {
-          cudaError_t fe = run_fused_block(ctx, dst, cur, f, ctx->net[i + 1], n, L[i].hin, L[i].hin, L[i].stride);
+          cudaError_t fe = run_fused_block(ctx, dst, cur, f, ctx->net[i + 1], n, L[i].hin, L[i].hin, L[i].stride, mnv1::switches().fused_pair);
           if (fe != cudaErrorNotSupported) {
             e = fe;
             cur = dst; side ^= 1;
@@ -1126,7 +1129,7 @@ int mnv1_dw_pw_block(mnv1_ctx* ctx, mnv1_buf* out, const mnv1_buf* in, const mnv
   if (rc) return rc;
   if (in->n != out->n) return fail(ctx, MNV1_EINVAL, "dw_pw_block: batch mismatch");
   TimedLaunch tl(ctx);
-  cudaError_t e = run_fused_block(ctx, out->d, in->d, dw, pw, in->n, rows, cols, stride);
+  cudaError_t e = run_fused_block(ctx, out->d, in->d, dw, pw, in->n, rows, cols, stride, true);
   if (e == cudaErrorNotSupported) return fail(ctx, MNV1_EUNSUPPORTED, "dw_pw_block: no fused variant for this shape");
   if (e != cudaSuccess) return fail_cuda(ctx, e, "dw_pw_block");
   return MNV1_OK;
@@ -1142,7 +1145,7 @@ int mnv1_fused_layers(mnv1_ctx* ctx, int* fused) {
     fused[i] = 0;
     if (ctx->use_fused && ctx->dtype == MNV1_BF16 && L[i].kind == MNV1_DEPTHWISE && i + 1 < MNV1_NUM_LAYERS &&
         L[i + 1].kind == MNV1_POINTWISE)
-      fused[i] = (mnv1::fused_pair_supported(ctx->net[i], ctx->net[i + 1], L[i].hin, L[i].hin, L[i].stride) ||
+      fused[i] = ((mnv1::switches().fused_pair && mnv1::fused_pair_supported(ctx->net[i], ctx->net[i + 1], L[i].hin, L[i].hin, L[i].stride)) ||
                   mnv1::fused_dw_pw_supported(ctx->net[i], ctx->net[i + 1], L[i].hin, L[i].hin, L[i].stride)) ? 1 : 0;
   }
   return MNV1_OK;

@@ -32,14 +32,14 @@ namespace {
 
 using namespace ptx;
 
-constexpr int FP_GW = 4;            // warps per stencil group
 constexpr int FP_EPI_WARPS = 4;     // one per TMEM lane quarter
 constexpr int FP_TP = 16;           // TMEM-lane pitch of a tile row
 constexpr uint32_t FP_A_BYTES = 128 * 128;    // A stage: 128 rows x 64 bf16, 128B swizzle
 constexpr uint32_t FP_BH_BYTES = 128 * 128;   // B stage: this CTA's 128 filter rows x 64 bf16
 
-template <int S_, int NKB_, int COUT_, int H_, int TWO_, int R_, int TW_, int RC_, int NG_, int NIG_, int NA_, int NB_, int NSTG_>
+template <int S_, int NKB_, int COUT_, int H_, int TWO_, int R_, int TW_, int RC_, int NG_, int GW_, int NIG_, int NA_, int NB_, int NSTG_>
 struct FpCfg {
+  static constexpr int GW = GW_;   // warps per stencil group
   static constexpr int S = S_, NKB = NKB_, COUT = COUT_, H = H_, TWO = TWO_, R = R_, TW = TW_, RC = RC_;
   static constexpr int NG = NG_, NIG = NIG_, NI = NG_ * NIG_, NA = NA_, NB = NB_, NSTG = NSTG_;
   static constexpr int CK = 64, C = CK * NKB, NH = COUT / 256;
@@ -49,7 +49,7 @@ struct FpCfg {
   static constexpr int PG = TWO / TW, NCOL = (TW - 1) * S + 3, RING = S == 1 ? 3 : 2;
   static constexpr uint32_t CHUNK_BYTES = (uint32_t)RC * BW * 128;
   // warp roles: stencil groups first (lowest issue priority), then the epilogue, then the single-thread roles
-  static constexpr int W_EPI = NG * FP_GW, W_MMA = W_EPI + FP_EPI_WARPS, W_TMA = W_MMA + 1, W_BPROD = W_MMA + 2;
+  static constexpr int W_EPI = NG * GW, W_MMA = W_EPI + FP_EPI_WARPS, W_TMA = W_MMA + 1, W_BPROD = W_MMA + 2;
   static constexpr int WARPS = W_MMA + 4;   // the single-thread roles share the last warpgroup (one idle warp)
   static_assert(W_EPI % 4 == 0, "roles are dispatched per warpgroup");
   static constexpr int THREADS = WARPS * 32;
@@ -65,7 +65,7 @@ struct FpCfg {
   static constexpr size_t SMEM = 1024 + OFF_END;
   static_assert(COUT % 256 == 0 && NH >= 1 && NH <= 2, "Cout: 256 or 512 (two 256-column TMEM accumulators)");
   static_assert(R * FP_TP <= 128 && TWO <= FP_TP, "tile does not fit one UMMA M tile");
-  static_assert(HO % R == 0 && WO % TWO == 0 && TWO % TW == 0 && PG * 16 <= FP_GW * 32, "shape does not tile");
+  static_assert(HO % R == 0 && WO % TWO == 0 && TWO % TW == 0 && PG * 16 <= GW * 32, "shape does not tile");
   static_assert((BANDS * STRIPS) % 2 == 0, "the two CTAs of a pair take the two halves of an image");
   static_assert(NA >= NG && NIG >= 2 && NB >= 2, "an A stage per group at least; rings hold at least two entries");
   static_assert(CHUNK_BYTES % 128 == 0, "chunk pitch");
@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(Cfg::THREADS, 1)
 fused_pair_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_out2,
                   const __grid_constant__ FpParams p) {
+  constexpr int FP_GW = Cfg::GW;
   constexpr int S = Cfg::S, NKB = Cfg::NKB, NH = Cfg::NH, TWO = Cfg::TWO, R = Cfg::R, TW = Cfg::TW, C = Cfg::C;
   constexpr int RC = Cfg::RC, NG = Cfg::NG, NIG = Cfg::NIG, NI = Cfg::NI, NA = Cfg::NA, NB = Cfg::NB, NSTG = Cfg::NSTG;
   constexpr int HR = Cfg::HR, BW = Cfg::BW, NCHK = Cfg::NCHK, PG = Cfg::PG, NCOL = Cfg::NCOL, RING = Cfg::RING;
@@ -480,11 +481,20 @@ cudaError_t launch_fp(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
             : cudaLaunchKernelEx(&cfg, fused_pair_kernel<Cfg, false, false>, tin, tb, tout, tout2, p);
 }
 
-//                   S NKB COUT  H TWO R TW RC NG NIG NA NB NSTG
-using FpL14 = FpCfg<1, 8, 512, 14, 14, 7, 2, 3, 4, 2, 4, 4, 1>;   // 14x14x512 -> 14x14x512 (layers 14+15 ... 22+23)
+//                   S NKB COUT  H TWO R TW RC NG GW NIG NA NB NSTG
+#ifndef MNV1_FP_VARIANT
+#define MNV1_FP_VARIANT 0
+#endif
+#if MNV1_FP_VARIANT == 1     // two groups of 8 warps, one column per thread, two A stages per group
+using FpL14 = FpCfg<1, 8, 512, 14, 14, 7, 1, 3, 2, 8, 2, 4, 4, 2>;
+#elif MNV1_FP_VARIANT == 2   // the same with three A stages per group
+using FpL14 = FpCfg<1, 8, 512, 14, 14, 7, 1, 3, 2, 8, 3, 6, 3, 1>;
+#else                        // four groups of 4 warps, one A stage per group
+using FpL14 = FpCfg<1, 8, 512, 14, 14, 7, 2, 3, 4, 4, 2, 4, 4, 1>;
+#endif   // 14x14x512 -> 14x14x512 (layers 14+15 ... 22+23)
 
 bool fp_match(const mnv1_filter* dw, const mnv1_filter* pw, int rows, int cols, int stride) {
-  if (switches().no_fused_pair || !dw->w_scaled || !pw->w_bf16 || pw->cin != dw->cout) return false;
+  if (!dw->w_scaled || !pw->w_bf16 || pw->cin != dw->cout) return false;
   return stride == FpL14::S && dw->cout == FpL14::C && pw->cout == FpL14::COUT && rows == FpL14::H && cols == FpL14::H;
 }
 

@@ -457,11 +457,13 @@ def test_fused_block_unsupported_shape(mn):
 
 
 def test_fused_layers_report(mn, synth_net):
-    """mnv1_fused_layers: a bf16 context fuses layers 2-11 (resident filter) and 14-23 (CTA pairs, streamed filter)
-    pairwise inside mnv1_forward, an fp32 context nothing"""
+    """mnv1_fused_layers: a bf16 context fuses layers 2-11 pairwise inside mnv1_forward (14-23 too with MNV1_FUSED_PAIR=1:
+    the CTA-pair kernel is correct but slower than its two kernels), an fp32 context nothing"""
+    import os
     c = _net_ctx(mn, mn.BF16, synth_net)
     f = c.fused_layers()
-    assert [i + 1 for i in range(29) if f[i]] == [2, 4, 6, 8, 10, 14, 16, 18, 20, 22]
+    want = [2, 4, 6, 8, 10] + ([14, 16, 18, 20, 22] if os.environ.get("MNV1_FUSED_PAIR") else [])
+    assert [i + 1 for i in range(29) if f[i]] == want
     c.use_fused_blocks(False)
     assert not c.fused_layers().any()
     c.close()
