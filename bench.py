@@ -206,32 +206,20 @@ def h2d_ceiling(ctx, torch, dev, nbytes, world, dist):
     (mnv1_h2d_probe: 20 copies of one batch back to back, CUDA events): the ceiling of the e2e number."""
     if world > 1:
         dist.barrier()
-    g = torch.tensor([ctx.h2d_probe(nbytes, 20)], dtype=torch.float64, device=dev)
+    g = torch.tensor([ctx.h2d_probe(nbytes, 21)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(g, op=dist.ReduceOp.SUM)     # ranks copy concurrently: the box's aggregate
     return float(g.item())
 
 
-def bind_to_gpu_numa(local):
-    """Keep this rank's threads (and so its first-touch pinned pages) on the CPUs next to its GPU."""
+def host_cpus():
+    """The GPU boxes of this pool expose ONE NUMA node (every GPU reports CPU affinity 0-31, NUMA 0: checked with
+    `nvidia-smi topo -m` and /sys/devices/system/node in round 2), so there is nothing to bind a rank to; report the
+    CPUs this rank may run on."""
     try:
-        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=10).stdout
-        for ln in out.splitlines():
-            f = ln.split()
-            if f and f[0] == f"GPU{local}":
-                for tok in f[1:]:
-                    if "-" in tok and tok.replace("-", "").replace(",", "").isdigit():
-                        cpus = set()
-                        for part in tok.split(","):
-                            a, b = part.split("-") if "-" in part else (part, part)
-                            cpus.update(range(int(a), int(b) + 1))
-                        cpus &= os.sched_getaffinity(0)
-                        if cpus:
-                            os.sched_setaffinity(0, cpus)
-                            return f"{tok} ({len(cpus)} cpus)"
-        return "no affinity column for this GPU"
-    except Exception as e:  # noqa: BLE001
-        return f"unavailable ({type(e).__name__})"
+        return f"{len(os.sched_getaffinity(0))} cpus, single NUMA node: no per-rank binding"
+    except Exception:  # noqa: BLE001
+        return "unknown"
 
 
 def run_ours(args):
@@ -247,7 +235,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the product path")
-    numa = bind_to_gpu_numa(local)
+    numa = host_cpus()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -470,7 +458,7 @@ def run_ours(args):
                        "timing": "wall clock, median of 3 repetitions of `steps` steps, max over ranks",
                        "blocking_call_value": round(e2e_blocking, 1),
                        "h2d_ceiling": {"gbs_all_ranks": round(ceiling_gbs, 1), "images_per_s": round(ceiling_imgs, 1),
-                                       "how": "mnv1_h2d_probe: pinned cudaMemcpyAsync of one batch, 20 back to back, CUDA events, all ranks at once (sum)"},
+                                       "how": "mnv1_h2d_probe: pinned cudaMemcpyAsync of one batch, 20 back to back over 3 rotating source buffers (the e2e working set), CUDA events, all ranks at once (sum)"},
                        "frac_of_min_kernel_or_h2d_ceiling": round(e2e_value / min(value, ceiling_imgs), 3)},
                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
                "comm": comm, "gather_check": gather_check, "configs": cfgs, "layers": rows}

@@ -2,6 +2,8 @@
 // points with kernel.cl's argument order, and the whole-network executor (activation arena +
 // CUDA graph) that replaces the 29 copy-pasted layer blocks of MobileNet.c:207-2763.
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -33,6 +35,7 @@ const mnv1::Switches& mnv1::switches() {
     sw.fused_head = getenv("MNV1_FUSED_HEAD") != nullptr;   // one cluster kernel for pool+FC+softmax: correct, still slower than the three launches
     sw.fused_pair = getenv("MNV1_FUSED_PAIR") != nullptr;   // layers 14-23 as CTA-pair fused blocks inside mnv1_forward*: correct, but
                                                              // stencil-bound at 67 us per block against 45 us for the two kernels
+    sw.pp_direct = getenv("MNV1_PP_DIRECT") != nullptr;
     sw.rb_mask = getenv("MNV1_RB_MASK") ? strtol(getenv("MNV1_RB_MASK"), nullptr, 0) : ~0L;
   });
   return sw;
@@ -1452,6 +1455,10 @@ int mnv1_profile_prefixes(mnv1_ctx* ctx, const void* d_images, int n, int iters,
       cudaEventRecord(evs[2 * j + 1], ctx->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    // A repetition is a ~10 ms burst; pausing between bursts keeps every one of them at the clocks a short timed
+    // loop sees (a B200 under a sustained load settles some 5 % lower under its power cap), so that the launch
+    // times add up to what `K` back-to-back steps measure.
+    std::this_thread::sleep_for(std::chrono::milliseconds(25));
     if (e != cudaSuccess || it < 0) continue;
     float prev = 0.f;
     for (int j = 0; j < nc; ++j) {
@@ -1476,27 +1483,34 @@ int mnv1_profile_prefixes(mnv1_ctx* ctx, const void* d_images, int n, int iters,
   return MNV1_OK;
 }
 
-// What a plain pinned cudaMemcpyAsync reaches on this box: `reps` back-to-back host-to-device copies of
-// `bytes` on the context's copy stream, CUDA events.  The ceiling of mnv1_forward's upload.
+// What a plain pinned cudaMemcpyAsync reaches on this box: `reps` back-to-back host-to-device copies of `bytes` on
+// the context's copy stream, CUDA events.  The copies rotate over THREE pinned source buffers, like the three
+// batches mnv1_forward_submit keeps in flight: a single buffer copied again and again is served from the CPU's
+// last-level cache and overstates what the host's DRAM can feed the link.  The ceiling of mnv1_forward's upload.
 int mnv1_h2d_probe(mnv1_ctx* ctx, size_t bytes, int reps, float* gbytes_per_s) {
   GUARD(ctx);
   if (!ctx || !bytes || reps <= 0 || !gbytes_per_s) return fail(ctx, MNV1_EINVAL, "h2d_probe: bad arguments");
-  void *h = nullptr, *d = nullptr;
+  void* h[3] = {nullptr, nullptr, nullptr};
+  void* d = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  cudaError_t e = cudaMallocHost(&h, bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d, bytes);
-  if (e == cudaSuccess) { memset(h, 1, bytes); e = cudaEventCreate(&e0); }
+  cudaError_t e = cudaMalloc(&d, bytes);
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+    e = cudaMallocHost(&h[i], bytes);
+    if (e == cudaSuccess) memset(h[i], i + 1, bytes);
+  }
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
   if (e == cudaSuccess) e = cudaEventCreate(&e1);
-  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaMemcpyAsync(d, h[i], bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
   if (e == cudaSuccess) e = cudaEventRecord(e0, ctx->copy_stream);
-  for (int i = 0; i < reps && e == cudaSuccess; ++i) e = cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+  for (int i = 0; i < reps && e == cudaSuccess; ++i) e = cudaMemcpyAsync(d, h[i % 3], bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
   if (e == cudaSuccess) e = cudaEventRecord(e1, ctx->copy_stream);
   if (e == cudaSuccess) e = cudaEventSynchronize(e1);
   float ms = 0.f;
   if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
-  cudaFree(d); cudaFreeHost(h);
+  cudaFree(d);
+  for (int i = 0; i < 3; ++i) cudaFreeHost(h[i]);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "h2d_probe");
   *gbytes_per_s = (float)((double)bytes * reps / (ms * 1e-3) / 1e9);
   return MNV1_OK;

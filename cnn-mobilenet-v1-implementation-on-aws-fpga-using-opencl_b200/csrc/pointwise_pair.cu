@@ -55,7 +55,11 @@ struct McParams {
   int dbg;      // MNV1_PP_DBG (timing experiments only): 1 = st.global from registers instead of staging + TMA store, 2 = no operand loads, 4 = no epilogue output
 };
 
-template <bool RELU>
+// DIRECT: the epilogue stores its bf16 rows straight from registers with 256-bit st.global (32 B = one full sector
+// per thread and instruction: no partial-sector writes) instead of staging them in shared memory for a TMA store —
+// the staging costs 128 KB of shared-memory traffic per tile (64 KB written, 64 KB read back by the TMA unit) on a
+// kernel whose shared-memory data pipe is ~93 % busy (profiles/r01_pp_l15_ncu.txt), and its 64 KB buy two more ring stages.
+template <bool RELU, bool DIRECT>
 __global__ void __launch_bounds__(MC_THREADS, 1)
 pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, const McParams p) {
@@ -64,8 +68,8 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   uint8_t* const smem_g = smem_raw + (smem - smem_u32(smem_raw));
   const int stages = p.stages;
   const uint32_t sRing = smem;
-  const uint32_t sOut = sRing + (uint32_t)stages * MC_STAGE_BYTES;          // 8 warps x 2 x 4 KB
-  const uint32_t sScale = sOut + MC_EPI_WARPS * 8192u;                      // [Cout] fp32
+  const uint32_t sOut = sRing + (uint32_t)stages * MC_STAGE_BYTES;          // 8 warps x 2 x 4 KB (not DIRECT)
+  const uint32_t sScale = sOut + (DIRECT ? 0u : MC_EPI_WARPS * 8192u);      // [Cout] fp32
   const uint32_t sShift = sScale + (uint32_t)p.Cout * 4u;
   const uint32_t bars = sShift + (uint32_t)p.Cout * 4u;
   const uint32_t full = bars, empty = full + 8u * MC_MAX_STAGES, tm_full = empty + 8u * MC_MAX_STAGES;
@@ -188,8 +192,10 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         ++blk;
         uint32_t v[32];
         tmem_ld32_nowait(taddr + (uint32_t)(b * 64), v);
-        if (lane == 0) tma_store_wait_read<1>();           // the store issued two blocks ago has consumed this buffer
-        __syncwarp();
+        if (!DIRECT) {
+          if (lane == 0) tma_store_wait_read<1>();         // the store issued two blocks ago has consumed this buffer
+          __syncwarp();
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           // this half's 32 scale / shift values first: their latency hides under the TMEM load
@@ -206,12 +212,14 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
           }
           if (half == 0) tmem_ld32_nowait(taddr + (uint32_t)(b * 64 + 32), v);   // second half under the stores
           if (MNV1_DBG(p.dbg) & 4) {
-          } else if (MNV1_DBG(p.dbg) & 1) {
+          } else if (DIRECT) {
             const long row = (long)m_idx + lane;
             if (row < p.M) {
-              uint4* gp = reinterpret_cast<uint4*>(p.out + row * p.Cout + n_idx + b * 64 + half * 32);
-#pragma unroll
-              for (int c4 = 0; c4 < 4; ++c4) gp[c4] = make_uint4(q[4 * c4], q[4 * c4 + 1], q[4 * c4 + 2], q[4 * c4 + 3]);
+              bf16* gp = p.out + row * p.Cout + n_idx + b * 64 + half * 32;
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gp), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]),
+                           "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]) : "memory");
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gp + 16), "r"(q[8]), "r"(q[9]), "r"(q[10]), "r"(q[11]),
+                           "r"(q[12]), "r"(q[13]), "r"(q[14]), "r"(q[15]) : "memory");
             }
           } else {
 #pragma unroll
@@ -219,7 +227,7 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
             sts128(sbuf + row_off + (((uint32_t)(4 * half + c4) ^ row_x) << 4), q[4 * c4], q[4 * c4 + 1], q[4 * c4 + 2], q[4 * c4 + 3]);
           }
         }
-        if (MNV1_DBG(p.dbg) & 5) continue;
+        if (DIRECT || (MNV1_DBG(p.dbg) & 4)) continue;
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {   // box = 64 columns x 32 rows; rows past M are clipped by the TMA unit
@@ -233,7 +241,7 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       if (threadIdx.x == 64) pp_stamp(MNV1_TRC(p.trace), 2, u / num_clusters, 2);
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (!DIRECT && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -271,14 +279,17 @@ cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* 
   if (e == cudaSuccess) e = encode_box(&tb, f->w_bf16, (uint64_t)cout, (uint64_t)k, 128, err);
   if (e == cudaSuccess) e = encode_box(&to, out, (uint64_t)m, (uint64_t)cout, 32, err);
   if (e != cudaSuccess) return e;
-  const size_t fixed = 1024 + MC_EPI_WARPS * 8192 + (size_t)cout * 8 + 16 * MC_MAX_STAGES + 64;
+  const bool direct = switches().pp_direct;
+  const size_t fixed = 1024 + (direct ? 0 : MC_EPI_WARPS * 8192) + (size_t)cout * 8 + 16 * MC_MAX_STAGES + 64;
   int stages = (int)((227 * 1024 - fixed) / MC_STAGE_BYTES);
   if (stages > MC_MAX_STAGES) stages = MC_MAX_STAGES;
   if (stages < 2) return cudaErrorNotSupported;
   const size_t smem = fixed + (size_t)stages * MC_STAGE_BYTES;
   {
-    e = ensure_dyn_smem((const void*)pointwise_pair_kernel<true>, 227 * 1024);
-    if (e == cudaSuccess) e = ensure_dyn_smem((const void*)pointwise_pair_kernel<false>, 227 * 1024);
+    e = ensure_dyn_smem((const void*)pointwise_pair_kernel<true, false>, 227 * 1024);
+    if (e == cudaSuccess) e = ensure_dyn_smem((const void*)pointwise_pair_kernel<false, false>, 227 * 1024);
+    if (e == cudaSuccess) e = ensure_dyn_smem((const void*)pointwise_pair_kernel<true, true>, 227 * 1024);
+    if (e == cudaSuccess) e = ensure_dyn_smem((const void*)pointwise_pair_kernel<false, true>, 227 * 1024);
     if (e != cudaSuccess) return e;
   }
   McParams p{};
@@ -310,8 +321,12 @@ cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* 
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  e = f->act != MNV1_ACT_NONE ? cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<true>, ta, tb, to, p)
-                              : cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<false>, ta, tb, to, p);
+  if (direct)
+    e = f->act != MNV1_ACT_NONE ? cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<true, true>, ta, tb, to, p)
+                                : cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<false, true>, ta, tb, to, p);
+  else
+    e = f->act != MNV1_ACT_NONE ? cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<true, false>, ta, tb, to, p)
+                                : cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<false, false>, ta, tb, to, p);
 #ifdef MNV1_TRACE
   if (trace_path && e == cudaSuccess) {   // dump the stamps of this launch
     std::vector<unsigned long long> hbuf(4 * 128 * 4);
