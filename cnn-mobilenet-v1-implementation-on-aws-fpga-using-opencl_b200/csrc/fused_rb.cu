@@ -61,8 +61,13 @@ struct RbCfg {
   static constexpr uint32_t CHUNK_BYTES = (uint32_t)RC * BW * LINE;
   static constexpr uint32_t CHUNK_PITCH = (CHUNK_BYTES + 127u) & ~127u;
   static constexpr uint32_t B_BYTES = (uint32_t)COUT * 128;   // one k-block of the filter
-  static constexpr int WARPS = 2 + NE * RB_EPI_WARPS + NG * GW;
+  // More than 20 warps do not fit 96 registers each: the block is then launched with 80 per thread and setmaxnreg
+  // moves registers from the single-thread roles and the epilogue to the stencil warps (REGSPLIT).  setmaxnreg is
+  // warpgroup-wide, so the two single-thread roles get a warpgroup of their own (two idle warps).
+  static constexpr bool REGSPLIT = 2 + NE * RB_EPI_WARPS + NG * GW > 20;
+  static constexpr int WARPS = REGSPLIT ? NG * GW + NE * RB_EPI_WARPS + 4 : 2 + NE * RB_EPI_WARPS + NG * GW;
   static constexpr int THREADS = WARPS * 32;
+  static_assert(!REGSPLIT || (GW % 4 == 0 && WARPS == 24), "register split is laid out for 16 stencil + 4 epilogue + 4 role warps");
   static constexpr int NACC = 512 / COUT > 8 ? 8 : 512 / COUT;   // TMEM accumulator stages of COUT columns
   static constexpr int NBAR = 2 * NI + 2 * NA + 2 * NACC + 1;
   static constexpr uint32_t OFF_B = 0;
@@ -158,7 +163,11 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   const int total_units = nt * NKB;
   const int per_img = p.bands * p.strips;
 
-  if (warp == W_TMA) {
+  // REGSPLIT: 768 threads x 80 registers = 61440 = 512 x 88 (stencil) + 128 x 72 (epilogue) + 128 x 56 (roles); every
+  // setmaxnreg sits at the top of the branch whose code it governs (ptxas allocates per dominated region)
+  if (warp >= W_MMA) {
+   if constexpr (Cfg::REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+   if (warp == W_TMA) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       mbar_expect_tx(b_full, NKB * Cfg::B_BYTES);
@@ -194,7 +203,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         }
       }
     }
-  } else if (warp == W_MMA) {
+   } else if (warp == W_MMA) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16_m128(COUT);
@@ -223,8 +232,10 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
         umma_commit(tm_full + 8u * acc);
       }
     }
+   }
   } else if (warp >= W_EPI) {
     // ======================= epilogue warps =======================
+    if constexpr (Cfg::REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     // A warp owns TMEM lanes 32*quarter .. +31 = tile rows 2*quarter, 2*quarter+1 and works on its own:
     // private staging (NSTG x 4 KB) and its own TMA stores, so the four warps never meet.
     const int quarter = warp & 3;                          // TMEM lane quarter = warp % 4
@@ -298,6 +309,7 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
     if (lane == 0) tma_store_wait_all();
   } else {
     // ======================= stencil groups =======================
+    if constexpr (Cfg::REGSPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int g = warp / GW;
     const int t = tid - g * GW * 32;                      // thread index inside the group
     const bool active = t < PG * CQ;
@@ -490,6 +502,8 @@ cudaError_t launch_rb(bf16* out, const bf16* in, const mnv1_filter* dw, const mn
 using CfgL02 = RbCfg<1, 32, 1,  64, 16, 8, 2, 10, 4, 2, 2, 4, 2, 1>;   // 112x112x32  -> 112x112x64
 using CfgL04 = RbCfg<2, 64, 1, 128, 14, 8, 2,  2, 3, 4, 5, 3, 1, 2>;   // 112x112x64  -> 56x56x128
 using CfgL06 = RbCfg<1, 64, 2, 128, 14, 8, 2,  5, 3, 4, 3, 3, 1, 2>;   // 56x56x128   -> 56x56x128
+// (four stencil groups = 16 warps at 88 registers through the REGSPLIT path measured 121-134 us against 107 us for
+//  this three-group configuration, eager timing: the stencil is not short of warps; experiments/README.md)
 using CfgL08 = RbCfg<2, 64, 2, 256, 14, 7, 2,  2, 3, 4, 4, 3, 1, 1>;   // 56x56x128   -> 28x28x256
 using CfgL10 = RbCfg<1, 64, 4, 256, 14, 7, 2,  3, 2, 4, 3, 2, 1, 1>;   // 28x28x256   -> 28x28x256
 

@@ -12,9 +12,12 @@
  * reference copies them to the host and back, :306,340,350); pass -dump to get its per-layer
  * "Layer k op:" prints (:317-320) from a download.
  *
- * usage: prog [-w weights_file] [-i image.ppm] [-bf16] [-raw] [-ref-pad] [-dump] [-n batch]
+ * usage: prog [-w weights_file] [-i image.ppm] [-bf16 | -u8 [-wrap]] [-raw] [-ref-pad] [-dump] [-n batch]
  *   -w   weight file, default weights_c.txt (MobileNet.c:37); text or MNV1WTS1 binary
  *   -i   P6 PPM 224x224, default Cat_Image0.ppm (MobileNet.c:215)
+ *   -u8  the reference's own integer arithmetic (u8 maps x int8 filters -> int -> ReLU -> u8, kernel.cl:2-3,62,94;
+ *        implies -raw; the weight file must hold integers in [-128, 127]); -wrap stores like kernel.cl does
+ *        (the C conversion to unsigned char, modulo 256) instead of saturating
  *   -raw keep u8 pixels as integers (what kernel.cl reads) instead of x/127.5-1
  *   -ref-pad  pad stride-2 layers top/left (kernel.cl's `< 0` test) instead of TF "SAME"
  */
@@ -43,16 +46,18 @@ int mobilenet_run(int num_layers, int argc, char** argv) {
   const char* weights_path = "weights_c.txt";
   const char* image_path = "Cat_Image0.ppm";
   mnv1_dtype dtype = MNV1_F32;
-  int raw = 0, ref_pad = 0, dump = 0, batch = 1;
+  int raw = 0, ref_pad = 0, dump = 0, batch = 1, wrap = 0;
   for (int a = 1; a < argc; ++a) {
     if (!strcmp(argv[a], "-w") && a + 1 < argc) weights_path = argv[++a];
     else if (!strcmp(argv[a], "-i") && a + 1 < argc) image_path = argv[++a];
     else if (!strcmp(argv[a], "-bf16")) dtype = MNV1_BF16;
+    else if (!strcmp(argv[a], "-u8")) { dtype = MNV1_U8; raw = 1; }
+    else if (!strcmp(argv[a], "-wrap")) wrap = 1;
     else if (!strcmp(argv[a], "-raw")) raw = 1;
     else if (!strcmp(argv[a], "-ref-pad")) ref_pad = 1;
     else if (!strcmp(argv[a], "-dump")) dump = 1;
     else if (!strcmp(argv[a], "-n") && a + 1 < argc) batch = atoi(argv[++a]);
-    else { printf("usage: %s [-w weights] [-i image.ppm] [-bf16] [-raw] [-ref-pad] [-dump] [-n batch]\n", argv[0]); return 2; }
+    else { printf("usage: %s [-w weights] [-i image.ppm] [-bf16 | -u8 [-wrap]] [-raw] [-ref-pad] [-dump] [-n batch]\n", argv[0]); return 2; }
   }
   if (batch < 1) batch = 1;
 
@@ -64,6 +69,7 @@ int mobilenet_run(int num_layers, int argc, char** argv) {
   }
   CHECK(mnv1_ctx_set_pad_mode(ctx, ref_pad ? MNV1_PAD_REF : MNV1_PAD_TFSAME));
   if (!raw) CHECK(mnv1_ctx_set_input_transform(ctx, 1.0f / 127.5f, -1.0f));
+  if (dtype == MNV1_U8) CHECK(mnv1_ctx_set_u8_store(ctx, wrap));
 
   /* filter values for the whole network, parsed once (readSquezeNetKernel, MobileNet.c:31-47) */
   float* weights = (float*)malloc(sizeof(float) * MNV1_TOTAL_WEIGHTS);
@@ -110,10 +116,12 @@ int mobilenet_run(int num_layers, int argc, char** argv) {
     int rows = l->hin, cols = l->hin, filtersize = K;
     mnv1_filter* d_filter = NULL;
     mnv1_buf* d_output = NULL;
-    const int fc = l->kind == MNV1_FC;
+    /* integer contexts: every layer, the FC included, is the reference's `if (sum <= 0) sum = 0` (kernel.cl:52,87,109) */
+    const int fc = l->kind == MNV1_FC && dtype != MNV1_U8;
+    const mnv1_act act = dtype == MNV1_U8 ? MNV1_ACT_RELU : MNV1_ACT_RELU6;
     if (l->kind != MNV1_POOL)
       CHECK(mnv1_filter_create(ctx, (mnv1_kind)l->kind, weights + l->w_off, l->cin, l->cout, fc ? NULL : scale + l->c_off,
-                               shift + l->c_off, fc ? MNV1_ACT_NONE : MNV1_ACT_RELU6, &d_filter));
+                               shift + l->c_off, fc ? MNV1_ACT_NONE : act, &d_filter));
     CHECK(mnv1_malloc(ctx, batch, op_size, l->hout, l->hout, &d_output));
     switch (l->kind) {
       case MNV1_CONVOLUTE: /* MobileNet.c:208-315 */

@@ -59,3 +59,26 @@ def test_host_program_fails_loudly_without_inputs(tmp_path):
     subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
     r = subprocess.run([os.path.join(HOST, "out_l5")], cwd=tmp_path, capture_output=True, text=True, timeout=60)
     assert r.returncode != 0 and "Error:" in r.stdout
+
+
+@pytest.mark.gpu
+def test_host_program_integer_mode_matches_kernel_cl_arithmetic(tmp_path, oracle_mod):
+    """`out -u8 -wrap -ref-pad` with a weight file in the reference's own TEXT format (whitespace-separated decimal
+    integers, readSquezeNetKernel MobileNet.c:31-47): the 29-layer schedule in kernel.cl's arithmetic — u8 maps, int
+    filters, `if (sum <= 0) sum = 0`, the store to unsigned char wrapping modulo 256.  The printed top-1 must be
+    the oracle's (integer mode, wrapping store) for the same image and weights."""
+    subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
+    img = synth.images(1)
+    (tmp_path / "Cat_Image0.ppm").write_bytes(b"P6\n224 224\n255\n" + img[0].tobytes())
+    w = synth.kat_ints(5, 4209088, -3, 3).astype(np.int32)
+    with open(tmp_path / "weights_c.txt", "w") as f:           # the reference's format: one token per value
+        f.write("\n".join(str(int(v)) for v in w))
+    r = subprocess.run([os.path.join(HOST, "out"), "-u8", "-wrap", "-ref-pad"], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"Highest Probability of the element is present at location (\d+) and it's value is ([0-9.]+)\.", r.stdout)
+    assert m, r.stdout
+    logits, _ = oracle_mod.forward(img, w.astype(np.float32), None, None, pad_mode=oracle_mod.PAD_REF, act=oracle_mod.ACT_RELU,
+                                   rbf16=oracle_mod.STORE_U8_WRAP, in_scale=1.0, in_bias=0.0)
+    _, otop1, op1 = oracle_mod.softmax_argmax(logits)
+    assert int(m.group(1)) == int(otop1[0]) + 1
+    assert abs(float(m.group(2)) - float(op1[0])) < 1e-3

@@ -12,6 +12,16 @@ import subprocess
 import sys
 
 
+def base_name(name: str) -> str:
+    """the kernel's bare name, as mnv1_last_kernel_name / bench.py's rows call it"""
+    for k in ("stem_rows_kernel", "stem_tc_kernel", "fused_pair_kernel", "depthwise_tma_kernel", "depthwise_ring_kernel",
+              "depthwise_cw_kernel", "pointwise_pair_kernel", "pointwise_tc_kernel", "head_fused_kernel"):
+        if name.startswith(k): return "head" if k == "head_fused_kernel" else k
+    if name.startswith("fused_rb_kernel"): return "fused_dw_pw_kernel"
+    if name.startswith(("pool_kernel", "fc_mma_kernel", "softmax_kernel", "fc_kernel")): return "head"
+    return name.split("<")[0].strip()
+
+
 def family(name: str) -> str:
     if "fused_rb" in name: return "dw+pw"
     if "stem" in name: return "stem"
@@ -39,7 +49,7 @@ def main(rep, table, traffic=None):
     out = ["# one forward pass (batch 256, bf16) under `ncu --set full --clock-control none`",
            "# per launch: duration (cold-cache, serialised), DRAM bytes read / written, tensor-pipe active %, issue-slot %",
            f"{'kernel':78s} {'us':>6s} {'rd_MB':>8s} {'wr_MB':>8s} {'tensor%':>8s} {'issue%':>7s} {'regs':>5s}"]
-    fam = {}
+    fam, kern = {}, {}
     for r in rows[2:]:
         name = re.sub(r"^void |mnv1::|<unnamed>::|unnamed>::|\(anonymous namespace\)::", "", r[col["Kernel Name"]]).split("(")[0]
         us = num(r, "gpu__time_duration.sum")
@@ -52,6 +62,8 @@ def main(rep, table, traffic=None):
         out.append(f"{name[:78]:78s} {us:6.1f} {rd / 1e6:8.1f} {wr / 1e6:8.1f} {tens:8.1f} {issue:7.1f} {regs:5d}")
         f = fam.setdefault(family(name), {"launches": 0, "bytes": 0.0, "us": 0.0})
         f["launches"] += 1; f["bytes"] += rd + wr; f["us"] += us
+        k = kern.setdefault(base_name(name), {"launches": 0, "bytes": 0.0, "us": 0.0})
+        k["launches"] += 1; k["bytes"] += rd + wr; k["us"] += us
     open(table, "w").write("\n".join(out) + "\n")
     if traffic:
         # the bench's rows: "fc" = fc + softmax launches of one pass, every other family per launch
@@ -62,6 +74,8 @@ def main(rep, table, traffic=None):
             js[k] = int(per)
             detail[k] = {"launches": f["launches"], "dram_bytes_per_launch": int(per), "ncu_us_per_launch": round(f["us"] / (1 if k == "fc" else f["launches"]), 1)}
         js["detail"] = detail
+        # per distinct kernel (bench.py's roofline.kernels[].traffic): DRAM bytes per launch; "head" = its launches together
+        js["kernels"] = {k: int(v["bytes"] / (1 if k == "head" else v["launches"])) for k, v in kern.items()}
         json.dump(js, open(traffic, "w"), indent=1)
     print("\n".join(out[:6]))
 
