@@ -198,7 +198,46 @@ def config_latencies(mn, synth, dev_index):
         out[name] = {"batch": 1, "cuts": cuts, "per_launch_ms": per,
                      "timing": "median of 21 CUDA-graph replays of layers 1..k, CUDA events (mnv1_profile_prefixes)"}
         c.close()
+    out["u8"] = integer_mode_throughput(mn, synth, dev_index)
     return out
+
+
+def integer_mode_throughput(mn, synth, dev_index, batch=256, steps=10):
+    """The integer reference-faithful contexts (u8 x s8 -> s32, tcgen05 kind::i8 / DP4A; SURVEY 8(f) rank 3) on the same
+    batch-256 forward: seeded s8 filters with a per-layer requantisation shift, saturating store.  Reported, not tuned."""
+    import numpy as np
+    import torch
+    from mnv1_b200.layers import LAYERS, TOTAL_WEIGHTS, TOTAL_CHANNELS, DEPTHWISE, STEM, POOL
+    w = synth.kat_ints(99, TOTAL_WEIGHTS, -127, 127).astype(np.float32)
+    sc = np.ones(TOTAL_CHANNELS, np.float32)
+    sh = np.zeros(TOTAL_CHANNELS, np.float32)
+    for L in LAYERS:
+        if L.kind == POOL:
+            continue
+        fan = 27 if L.kind == STEM else 9 if L.kind == DEPTHWISE else L.cin
+        sc[L.c_off:L.c_off + L.cout] = 2.0 ** -int(np.ceil(np.log2(np.sqrt(fan) * 74 * 1.2)))
+    c = mn.Context(dev_index, mn.U8)
+    c.set_pad_mode(mn.PAD_TFSAME)
+    c.set_weights(w, sc, sh, mn.ACT_RELU)
+    c.plan(batch)
+    dev = f"cuda:{dev_index}"
+    img = torch.empty(batch * IMG_BYTES, dtype=torch.uint8, device=dev)
+    lg = torch.empty(batch, 1000, device=dev); t1 = torch.empty(batch, dtype=torch.int32, device=dev); p1 = torch.empty(batch, device=dev)
+    c.synth_images_device(img.data_ptr(), batch, 0, synth.IMAGE_SEED)
+    for _ in range(3):
+        c.forward_device(img.data_ptr(), batch, lg.data_ptr(), t1.data_ptr(), p1.data_ptr())
+    c.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        c.forward_device(img.data_ptr(), batch, lg.data_ptr(), t1.data_ptr(), p1.data_ptr())
+    c.sync()
+    dt = time.perf_counter() - t0
+    c.close()
+    return {"batch": batch, "images_per_s": round(batch * steps / dt, 1), "ms_per_step": round(dt / steps * 1e3, 3),
+            "arithmetic": "u8 activations x s8 filters -> s32 -> ReLU -> >> s -> saturating u8 store",
+            "timing": f"wall clock around {steps} graph replays after 3 warm-ups"}
 
 
 def h2d_ceiling(ctx, torch, dev, nbytes, world, dist):

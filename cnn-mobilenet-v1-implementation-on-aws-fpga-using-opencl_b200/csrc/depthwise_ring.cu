@@ -240,6 +240,8 @@ cudaError_t launch_dr(bf16* out, const bf16* in, const float* taps, const float*
 
 //                   S    C   H TWO R TW RC NG NIG
 using DrL14 = DrCfg<1,  512, 14, 14, 7, 2, 9, 4, 2>;   // 14x14x512
+// (round 2, tools/run_layer.py --layer 14: three groups 28.2 us, four 25.9-26.7, five 28.2 — the stencil is not short of
+//  warps; experiments/README.md)
 using DrL24 = DrCfg<2,  512, 14,  7, 7, 1, 15, 3, 2>;   // 14x14x512 -> 7x7
 
 }  // namespace
