@@ -36,6 +36,7 @@ const mnv1::Switches& mnv1::switches() {
     sw.fused_pair = getenv("MNV1_FUSED_PAIR") != nullptr;   // layers 14-23 as CTA-pair fused blocks inside mnv1_forward*: correct, but
                                                              // stencil-bound at 67 us per block against 45 us for the two kernels
     sw.pp_direct = getenv("MNV1_PP_DIRECT") != nullptr;
+    sw.no_pp_tail = getenv("MNV1_NO_PP_TAIL") != nullptr;
     sw.rb_mask = getenv("MNV1_RB_MASK") ? strtol(getenv("MNV1_RB_MASK"), nullptr, 0) : ~0L;
   });
   return sw;

@@ -67,6 +67,7 @@ struct RbCfg {
   static constexpr bool REGSPLIT = 2 + NE * RB_EPI_WARPS + NG * GW > 20;
   static constexpr int WARPS = REGSPLIT ? NG * GW + NE * RB_EPI_WARPS + 4 : 2 + NE * RB_EPI_WARPS + NG * GW;
   static constexpr int THREADS = WARPS * 32;
+  static constexpr int WARPS_TMA_ROLE = NG * GW + NE * RB_EPI_WARPS + 1;   // the TMA producer's warp (W_TMA in the kernel)
   static_assert(!REGSPLIT || (GW % 4 == 0 && WARPS == 24), "register split is laid out for 16 stencil + 4 epilogue + 4 role warps");
   static constexpr int NACC = 512 / COUT > 8 ? 8 : 512 / COUT;   // TMEM accumulator stages of COUT columns
   static constexpr int NBAR = 2 * NI + 2 * NA + 2 * NACC + 1;
@@ -155,6 +156,12 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = lds32(tmem_slot);
+  // The pointwise filter does not depend on the previous layer: its load is started BEFORE the wait, so that it
+  // travels while the last CTAs of the previous kernel are still running on other SMs.
+  if (warp == Cfg::WARPS_TMA_ROLE && lane == 0) {
+    mbar_expect_tx(b_full, NKB * Cfg::B_BYTES);
+    for (int kb = 0; kb < NKB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmap_b, b_full, kb * 64, 0);
+  }
   pdl_wait();                                            // the previous layer's output is complete and visible
 
   // this CTA's tiles: blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -170,8 +177,6 @@ fused_rb_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_consta
    if (warp == W_TMA) {
     // ======================= TMA producer =======================
     if (lane == 0) {
-      mbar_expect_tx(b_full, NKB * Cfg::B_BYTES);
-      for (int kb = 0; kb < NKB; ++kb) tma_load_2d(sB + kb * Cfg::B_BYTES, &tmap_b, b_full, kb * 64, 0);
       int stage[NG]; uint32_t phase[NG];                   // per-group ring position
 #pragma unroll
       for (int g = 0; g < NG; ++g) { stage[g] = 0; phase[g] = 0; }

@@ -50,6 +50,11 @@ struct McParams {
   uint32_t cap2;
   long M;
   int K, Cout, stages;
+  // Tail balancing: units [0, full_units) are whole 256 x 256 tiles; when the last round would be less than half full, its
+  // `tail_halves / 2` units are cut into 256 x 128 halves (N = 128 UMMAs) spread over twice as many clusters, so the
+  // launch ends after half a tile time instead of a whole one (392 units on 74 pairs: 5.5 rounds instead of 6).
+  long full_units;
+  int tail_halves;
   unsigned long long* trace;
   bf16* out;
   int dbg;      // MNV1_PP_DBG (timing experiments only): 1 = st.global from registers instead of staging + TMA store, 2 = no operand loads, 4 = no epilogue output
@@ -62,7 +67,7 @@ struct McParams {
 template <bool RELU, bool DIRECT>
 __global__ void __launch_bounds__(MC_THREADS, 1)
 pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_out, const McParams p) {
+                    const __grid_constant__ CUtensorMap tmap_b64, const __grid_constant__ CUtensorMap tmap_out, const McParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const smem_g = smem_raw + (smem - smem_u32(smem_raw));
@@ -82,15 +87,35 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int num_kb = p.K / MC_BK;
   const int n_tiles = p.Cout / 256;
   const long m_tiles = (p.M + 127) / 128, m_pairs = (m_tiles + 1) / 2;
-  const long num_units = m_pairs * n_tiles;     // a unit = (pair of m-tiles, n-tile); this CTA's m-tile is 2*pair + rank
+  // a unit = (pair of m-tiles, n-tile); this CTA's m-tile is 2*pair + rank.  Work item `it` of this cluster:
+  struct Work { long mp; int n_base, ncols; };
+  auto get_work = [&](long it, Work& w) -> bool {
+    const long u = cid + it * num_clusters;
+    if (u < p.full_units) { w.mp = u / n_tiles; w.n_base = (int)(u % n_tiles) * 256; w.ncols = 256; return true; }
+    const long hu = u - p.full_units;                      // the round after the last full one: half units
+    if (hu >= p.tail_halves) return false;
+    const long unit = p.full_units + (hu >> 1);
+    w.mp = unit / n_tiles; w.n_base = (int)(unit % n_tiles) * 256 + (int)(hu & 1) * 128; w.ncols = 128;
+    return true;
+  };
+  (void)m_pairs;
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_out);
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_b64); prefetch_tmap(&tmap_out);
     for (int s = 0; s < stages; ++s) { mbar_init(full + 8u * s, 1); mbar_init(empty + 8u * s, 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tm_full + 8u * a, 1); mbar_init(tm_empty + 8u * a, 2 * MC_EPI_WARPS); }
     mbar_init_fence();
   }
   if (warp == 1) tmem_alloc_pair(tmem_slot, 2 * MC_ACC_COLS);
+  {  // folded-BN scale / shift -> shared memory, before the wait below: filter constants do not depend on the previous layer
+    const int et = threadIdx.x - 64, n4 = p.Cout >> 2;
+    if (et >= 0 && et < n4) {
+      const float4 sv = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale) + et) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const float4 tv = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift) + et) : make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(smem_g + (sScale - smem))[et] = sv;
+      reinterpret_cast<float4*>(smem_g + (sShift - smem))[et] = tv;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();                             // the peer's barriers exist before anything is multicast to them
@@ -103,26 +128,30 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (lane == 0 && !(MNV1_DBG(p.dbg) & 2)) {
       const uint32_t full_leader = mapa_shared(full, 0);
       int stage = 0; uint32_t phase = 0;
-      for (long u = cid; u < num_units; u += num_clusters) {
-        const int m_idx = (int)((u / n_tiles) * 2 + rank) * 128;
+      Work w;
+      for (long it = 0; get_work(it, w); ++it) {
+        const int m_idx = (int)(w.mp * 2 + rank) * 128;
+        const uint32_t stage_tx = 2 * (MC_A_BYTES + (uint32_t)(w.ncols / 2) * 128u);   // both CTAs' A tile + filter half
         for (int kb = 0; kb < num_kb; ++kb) {
-          if (kb == 0) pp_stamp(MNV1_TRC(p.trace), 0, u / num_clusters, 0);
+          if (kb == 0) pp_stamp(MNV1_TRC(p.trace), 0, it, 0);
           mbar_wait(empty + 8u * stage, phase ^ 1u);       // the pair's MMAs that read this slot have retired
           const uint32_t sa = sRing + (uint32_t)stage * MC_STAGE_BYTES;
-          if (rank == 0) mbar_expect_tx(full + 8u * stage, 2 * MC_STAGE_BYTES);   // both CTAs' bytes complete on the leader's barrier
+          if (rank == 0) mbar_expect_tx(full + 8u * stage, stage_tx);   // both CTAs' bytes complete on the leader's barrier
           tma_load_2d_pair(sa, &tmap_a, full_leader + 8u * stage, kb * MC_BK, m_idx);
-          if (kb == num_kb - 1) pp_stamp(MNV1_TRC(p.trace), 0, u / num_clusters, 2);
+          if (kb == num_kb - 1) pp_stamp(MNV1_TRC(p.trace), 0, it, 2);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer (converged warp, one elected lane) =================
-    constexpr uint32_t idesc = umma_idesc_bf16_m256(256);
     const uint32_t elected = rank == 0 ? elect_one() : 0u;
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
-    for (long u = cid; rank == 0 && u < num_units; u += num_clusters) {   // the leader issues for the pair
+    Work w;
+    for (long it = 0; rank == 0 && get_work(it, w); ++it) {   // the leader issues for the pair
+      const long u = cid + it * num_clusters;
+      const uint32_t idesc = w.ncols == 256 ? umma_idesc_bf16_m256(256) : umma_idesc_bf16_m256(128);
       if (elected) pp_stamp(MNV1_TRC(p.trace), 1, u / num_clusters, 0);
       mbar_wait(tm_empty + 8u * as, aphase ^ 1u);          // epilogue has drained this accumulator stage
       tc_fence_after();
@@ -150,27 +179,19 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     if (lane == 0 && !(MNV1_DBG(p.dbg) & 2)) {
       const uint32_t full_leader = mapa_shared(full, 0);
       int stage = 0; uint32_t phase = 0;
-      for (long u = cid; u < num_units; u += num_clusters) {
-        const int n_idx = (int)(u % n_tiles) * 256 + (int)rank * 128;     // the half of the filter tile this CTA holds
+      Work w;
+      for (long it = 0; get_work(it, w); ++it) {
+        const int n_idx = w.n_base + (int)rank * (w.ncols / 2);           // the half of the filter (sub)tile this CTA holds
+        const CUtensorMap* tb = w.ncols == 256 ? &tmap_b : &tmap_b64;     // box of 128 or 64 filter rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty + 8u * stage, phase ^ 1u);
-          tma_load_2d_pair(sRing + (uint32_t)stage * MC_STAGE_BYTES + MC_A_BYTES, &tmap_b, full_leader + 8u * stage, kb * MC_BK, n_idx);
+          tma_load_2d_pair(sRing + (uint32_t)stage * MC_STAGE_BYTES + MC_A_BYTES, tb, full_leader + 8u * stage, kb * MC_BK, n_idx);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else {
     // ================= epilogue warps 2..9: independent, private staging =================
-    {
-      const int et = threadIdx.x - 64, n4 = p.Cout >> 2;
-      if (et < n4) {
-        const float4 sv = p.scale ? __ldg(reinterpret_cast<const float4*>(p.scale) + et) : make_float4(1.f, 1.f, 1.f, 1.f);
-        const float4 tv = p.shift ? __ldg(reinterpret_cast<const float4*>(p.shift) + et) : make_float4(0.f, 0.f, 0.f, 0.f);
-        reinterpret_cast<float4*>(smem_g + (sScale - smem))[et] = sv;
-        reinterpret_cast<float4*>(smem_g + (sShift - smem))[et] = tv;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * MC_EPI_WARPS) : "memory");
-    }
     const int quarter = warp & 3;                        // TMEM lanes 32*quarter .. +31
     const int h = (warp - 2) >> 2;                       // which 64-column blocks: b = h, h+2
     const uint32_t wbuf = sOut + (uint32_t)(warp - 2) * 8192u;
@@ -178,16 +199,19 @@ pointwise_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const uint32_t tm_empty_leader = mapa_shared(tm_empty, 0);
     int as = 0; uint32_t aphase = 0;
     uint32_t blk = 0;
-    for (long u = cid; u < num_units; u += num_clusters) {
-      const int m_idx = (int)((u / n_tiles) * 2 + rank) * 128 + quarter * 32;
-      const int n_idx = (int)(u % n_tiles) * 256;
+    Work w;
+    for (long it = 0; get_work(it, w); ++it) {
+      const long u = cid + it * num_clusters;
+      const int m_idx = (int)(w.mp * 2 + rank) * 128 + quarter * 32;
+      const int n_idx = w.n_base;
+      const int nblk = w.ncols / 64;
       if (threadIdx.x == 64) pp_stamp(MNV1_TRC(p.trace), 2, u / num_clusters, 0);
       mbar_wait(tm_full + 8u * as, aphase);
       tc_fence_after();
       if (threadIdx.x == 64) pp_stamp(MNV1_TRC(p.trace), 2, u / num_clusters, 1);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * MC_ACC_COLS;
 #pragma unroll 1
-      for (int b = h; b < 4; b += 2) {
+      for (int b = h; b < nblk; b += 2) {
         const uint32_t sbuf = wbuf + (blk & 1u) * 4096u;
         ++blk;
         uint32_t v[32];
@@ -274,9 +298,10 @@ cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* 
                                 cudaStream_t st, std::string* err) {
   if (switches().no_pair || !f->w_bf16 || cout % 256 || k % MC_BK || k < 256 || cout > 1024 || num_sms < 2) return cudaErrorNotSupported;
   if (m <= 0) return cudaSuccess;
-  CUtensorMap ta, tb, to;
+  CUtensorMap ta, tb, tb64, to;
   cudaError_t e = encode_box(&ta, in, (uint64_t)m, (uint64_t)k, 128, err);
   if (e == cudaSuccess) e = encode_box(&tb, f->w_bf16, (uint64_t)cout, (uint64_t)k, 128, err);
+  if (e == cudaSuccess) e = encode_box(&tb64, f->w_bf16, (uint64_t)cout, (uint64_t)k, 64, err);
   if (e == cudaSuccess) e = encode_box(&to, out, (uint64_t)m, (uint64_t)cout, 32, err);
   if (e != cudaSuccess) return e;
   const bool direct = switches().pp_direct;
@@ -310,6 +335,12 @@ cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* 
   const long m_tiles = (m + 127) / 128, units = ((m_tiles + 1) / 2) * (cout / 256);
   long clusters = num_sms / 2;
   if (clusters > units) clusters = units;
+  {
+    const long rem = units % clusters;
+    const bool split = rem > 0 && 2 * rem <= clusters && !switches().no_pp_tail;
+    p.full_units = split ? units - rem : units;
+    p.tail_halves = split ? (int)(2 * rem) : 0;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * clusters));
   cfg.blockDim = dim3(MC_THREADS);
@@ -322,11 +353,11 @@ cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   if (direct)
-    e = f->act != MNV1_ACT_NONE ? cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<true, true>, ta, tb, to, p)
-                                : cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<false, true>, ta, tb, to, p);
+    e = f->act != MNV1_ACT_NONE ? cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<true, true>, ta, tb, tb64, to, p)
+                                : cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<false, true>, ta, tb, tb64, to, p);
   else
-    e = f->act != MNV1_ACT_NONE ? cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<true, false>, ta, tb, to, p)
-                                : cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<false, false>, ta, tb, to, p);
+    e = f->act != MNV1_ACT_NONE ? cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<true, false>, ta, tb, tb64, to, p)
+                                : cudaLaunchKernelEx(&cfg, pointwise_pair_kernel<false, false>, ta, tb, tb64, to, p);
 #ifdef MNV1_TRACE
   if (trace_path && e == cudaSuccess) {   // dump the stamps of this launch
     std::vector<unsigned long long> hbuf(4 * 128 * 4);
