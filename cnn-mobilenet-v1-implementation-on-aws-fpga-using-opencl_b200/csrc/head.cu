@@ -183,13 +183,18 @@ __device__ __forceinline__ void split3(float x0, float x1, uint32_t& hi, uint32_
   mid = (m0 >> 16) | m1;
   lo = (__float_as_uint(s0) >> 16) | (__float_as_uint(s1) & 0xffff0000u);
 }
+// FCM_DEPTH k-steps of operand loads are kept in flight per warp: a warp's share of the contraction is only k/4 = 256 = 8
+// steps of 32, and with one step of prefetch every step exposed an L2 round trip (the kernel is latency-bound).
+#ifndef MNV1_FCM_DEPTH
+#define MNV1_FCM_DEPTH 4
+#endif
+constexpr int FCM_DEPTH = MNV1_FCM_DEPTH;
 __global__ void __launch_bounds__(FCM_WARPS * 32) fc_mma_kernel(float* __restrict__ out, const float* __restrict__ pooled,
                                                                 const bf16* __restrict__ w, const float* __restrict__ bias,
                                                                 int n, int k, int classes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   __shared__ float s_part[FCM_WARPS][16][FCM_NT * 8 + 1];
   pdl_trigger();
-  pdl_wait();
   const int img0 = blockIdx.y * 16, cls0 = blockIdx.x * (FCM_NT * 8);
   const int kw = k / FCM_WARPS, k_lo = warp * kw, k_hi = k_lo + kw;   // this warp's share of the contraction
   const int r0 = min(img0 + g, n - 1), r1 = min(img0 + g + 8, n - 1);       // clamped rows are computed, never stored
@@ -201,32 +206,43 @@ __global__ void __launch_bounds__(FCM_WARPS * 32) fc_mma_kernel(float* __restric
   float acc[FCM_NT][4];
 #pragma unroll
   for (int j = 0; j < FCM_NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-  float4 an[4];
-  uint4 bn[FCM_NT];
-  auto load = [&](int kb) {   // 32 contraction indices per step: this lane's are kb + 8t .. 8t+7
-    an[0] = __ldg(reinterpret_cast<const float4*>(a0p + kb)); an[1] = __ldg(reinterpret_cast<const float4*>(a0p + kb + 4));
-    an[2] = __ldg(reinterpret_cast<const float4*>(a1p + kb)); an[3] = __ldg(reinterpret_cast<const float4*>(a1p + kb + 4));
+  float4 an[FCM_DEPTH][4];
+  uint4 bn[FCM_DEPTH][FCM_NT];
+  // the filter rows do not depend on the previous kernel: their first FCM_DEPTH steps are requested before the wait
+  auto load_b = [&](int slot, int kb) {   // 32 contraction indices per step: this lane's are kb + 8t .. 8t+7
 #pragma unroll
-    for (int j = 0; j < FCM_NT; ++j) bn[j] = __ldg(reinterpret_cast<const uint4*>(bp[j] + kb));
+    for (int j = 0; j < FCM_NT; ++j) bn[slot][j] = __ldg(reinterpret_cast<const uint4*>(bp[j] + kb));
   };
-  load(k_lo);
-  for (int kb = k_lo; kb < k_hi; kb += 32) {
-    const float4 a00 = an[0], a01 = an[1], a10 = an[2], a11 = an[3];
-    uint4 b[FCM_NT];
+  auto load_a = [&](int slot, int kb) {
+    an[slot][0] = __ldg(reinterpret_cast<const float4*>(a0p + kb)); an[slot][1] = __ldg(reinterpret_cast<const float4*>(a0p + kb + 4));
+    an[slot][2] = __ldg(reinterpret_cast<const float4*>(a1p + kb)); an[slot][3] = __ldg(reinterpret_cast<const float4*>(a1p + kb + 4));
+  };
 #pragma unroll
-    for (int j = 0; j < FCM_NT; ++j) b[j] = bn[j];
-    if (kb + 32 < k_hi) load(kb + 32);
-    // MMA slot k = (2t, 2t+1 | 2t+8, 2t+9) of step s <- this lane's elements (4s, 4s+1 | 4s+2, 4s+3)
-    uint32_t ah[2][4], am[2][4], al[2][4];
-    split3(a00.x, a00.y, ah[0][0], am[0][0], al[0][0]); split3(a10.x, a10.y, ah[0][1], am[0][1], al[0][1]);
-    split3(a00.z, a00.w, ah[0][2], am[0][2], al[0][2]); split3(a10.z, a10.w, ah[0][3], am[0][3], al[0][3]);
-    split3(a01.x, a01.y, ah[1][0], am[1][0], al[1][0]); split3(a11.x, a11.y, ah[1][1], am[1][1], al[1][1]);
-    split3(a01.z, a01.w, ah[1][2], am[1][2], al[1][2]); split3(a11.z, a11.w, ah[1][3], am[1][3], al[1][3]);
+  for (int d = 0; d < FCM_DEPTH; ++d) load_b(d, k_lo + 32 * d);      // k / FCM_WARPS is a multiple of 32 * FCM_DEPTH (launch_fc)
+  pdl_wait();
 #pragma unroll
-    for (int j = 0; j < FCM_NT; ++j) {
-      mma_bf16_16816(acc[j], al[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], al[1], b[j].z, b[j].w);   // small pieces first
-      mma_bf16_16816(acc[j], am[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], am[1], b[j].z, b[j].w);
-      mma_bf16_16816(acc[j], ah[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], ah[1], b[j].z, b[j].w);
+  for (int d = 0; d < FCM_DEPTH; ++d) load_a(d, k_lo + 32 * d);
+  for (int kb0 = k_lo; kb0 < k_hi; kb0 += 32 * FCM_DEPTH) {
+#pragma unroll
+    for (int d = 0; d < FCM_DEPTH; ++d) {
+      const int kb = kb0 + 32 * d;
+      const float4 a00 = an[d][0], a01 = an[d][1], a10 = an[d][2], a11 = an[d][3];
+      uint4 b[FCM_NT];
+#pragma unroll
+      for (int j = 0; j < FCM_NT; ++j) b[j] = bn[d][j];
+      if (kb + 32 * FCM_DEPTH < k_hi) { load_b(d, kb + 32 * FCM_DEPTH); load_a(d, kb + 32 * FCM_DEPTH); }
+      // MMA slot k = (2t, 2t+1 | 2t+8, 2t+9) of step s <- this lane's elements (4s, 4s+1 | 4s+2, 4s+3)
+      uint32_t ah[2][4], am[2][4], al[2][4];
+      split3(a00.x, a00.y, ah[0][0], am[0][0], al[0][0]); split3(a10.x, a10.y, ah[0][1], am[0][1], al[0][1]);
+      split3(a00.z, a00.w, ah[0][2], am[0][2], al[0][2]); split3(a10.z, a10.w, ah[0][3], am[0][3], al[0][3]);
+      split3(a01.x, a01.y, ah[1][0], am[1][0], al[1][0]); split3(a11.x, a11.y, ah[1][1], am[1][1], al[1][1]);
+      split3(a01.z, a01.w, ah[1][2], am[1][2], al[1][2]); split3(a11.z, a11.w, ah[1][3], am[1][3], al[1][3]);
+#pragma unroll
+      for (int j = 0; j < FCM_NT; ++j) {
+        mma_bf16_16816(acc[j], al[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], al[1], b[j].z, b[j].w);   // small pieces first
+        mma_bf16_16816(acc[j], am[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], am[1], b[j].z, b[j].w);
+        mma_bf16_16816(acc[j], ah[0], b[j].x, b[j].y); mma_bf16_16816(acc[j], ah[1], b[j].z, b[j].w);
+      }
     }
   }
 #pragma unroll
@@ -255,7 +271,7 @@ cudaError_t launch_fc(float* out, const float* pooled, const float* w_f32, const
     if (e != cudaSuccess) return e;
   }
   if (smem > 96 * 1024) return cudaErrorNotSupported;
-  if (w_bf16 && k % (32 * FCM_WARPS) == 0) {   // bf16 filter: tensor cores, exact fp32 activations (three bf16 pieces)
+  if (w_bf16 && k % (32 * FCM_WARPS * FCM_DEPTH) == 0) {   // bf16 filter: tensor cores, exact fp32 activations (three bf16 pieces)
     dim3 g2((classes + FCM_NT * 8 - 1) / (FCM_NT * 8), (n + 15) / 16);
     return launch_pdl(fc_mma_kernel, g2, dim3(FCM_WARPS * 32), 0, st, out, pooled, w_bf16, bias, n, k, classes);
   }
