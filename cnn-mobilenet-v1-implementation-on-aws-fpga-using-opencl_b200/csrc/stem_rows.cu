@@ -75,7 +75,8 @@ struct StemRowsParams {
 
 template <bool RELU>
 __global__ void __launch_bounds__(SR_THREADS, 3)
-stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ StemRowsParams p) {
+stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_tail,
+                 const __grid_constant__ StemRowsParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem;                         // 2 x 16 KB
@@ -111,7 +112,7 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
       sts128(sB + tid * 128 + ((c ^ (tid & 7)) << 4), wv[4 * c], wv[4 * c + 1], wv[4 * c + 2], wv[4 * c + 3]);
   }
   if (tid == 0) {
-    prefetch_tmap(&tmap_out);
+    prefetch_tmap(&tmap_out); prefetch_tmap(&tmap_tail);
     for (int b = 0; b < SR_NA; ++b) { mbar_init(a_full + 8 * b, 128); mbar_init(mma_done + 8 * b, 1); mbar_init(tmem_free + 8 * b, 4); }
     for (int s = 0; s < SR_NI; ++s) { mbar_init(in_full + 8 * s, 1); mbar_init(in_empty + 8 * s, 4); }
     mbar_init_fence();
@@ -200,11 +201,15 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
     }
   } else if (warp < 8) {
     // ======================= epilogue warps =======================
+    // Each warp owns 32 pixels of the row and works on its own: private double-buffered staging (2 x 2 KB, 64B
+    // swizzle) and its own TMA store of exactly its valid pixels (box of 32 pixels, or the row's remainder for the
+    // last warp) — no block-level barrier and no single storing thread between the four warps.
     const int q = warp & 3, row = q * 32 + lane;
-    const bool leader = tid == 128;
+    const int vr = Wo - 32 * q < 0 ? 0 : (Wo - 32 * q > 32 ? 32 : Wo - 32 * q);   // valid pixels of this warp
+    const uint32_t wbuf = sO + (uint32_t)q * 4096u;
     int i = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
-      const int buf = i % SR_NA, k = i / SR_NA, sbuf = i & 1;
+      const int buf = i % SR_NA, k = i / SR_NA;
       mbar_wait(mma_done + 8 * buf, (uint32_t)k & 1u);
       tc_fence_after();
       uint32_t v[32];
@@ -213,10 +218,11 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_free + 8 * buf);
-      // staging buffer `sbuf` was read by the TMA store of tile i-2
-      if (leader) tma_store_wait_read<1>();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const uint32_t orow = sO + sbuf * SR_O_BYTES + row * 64;
+      if (vr == 0) continue;
+      // this warp's staging buffer (i & 1) was read by its TMA store of tile i-2
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
+      const uint32_t orow = wbuf + (uint32_t)(i & 1) * 2048u + (uint32_t)lane * 64u;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t o[4];
@@ -229,13 +235,13 @@ stem_rows_kernel(const __grid_constant__ CUtensorMap tmap_out, const __grid_cons
         sts128(orow + ((c ^ ((row >> 1) & 3)) << 4), o[0], o[1], o[2], o[3]);   // SWIZZLE_64B
       }
       fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (leader) {
-        tma_store_2d(&tmap_out, sO + sbuf * SR_O_BYTES, 0, t * Wo);
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(vr == 32 ? &tmap_out : &tmap_tail, wbuf + (uint32_t)(i & 1) * 2048u, 0, t * Wo + 32 * q);
         tma_store_commit();
       }
     }
-    if (leader) tma_store_wait_all();
+    if (lane == 0) tma_store_wait_all();
   } else if (warp == 8) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
@@ -302,13 +308,17 @@ cudaError_t launch_stem_rows(bf16* out, const StemArgs& a, const __half* wq_dev,
   p.cap2 = act == MNV1_ACT_RELU6 ? 0x40c040c0u : 0x7f807f80u;
   const unsigned short ph = __half_as_ushort(__float2half_rn(p0));
   p.pad_f16x2 = (uint32_t)ph | ((uint32_t)ph << 16);
-  CUtensorMap tm;
+  CUtensorMap tm, tm_tail;
   cuuint64_t gdim[2] = {(cuuint64_t)SR_C, (cuuint64_t)m_total};
   cuuint64_t gstr[1] = {(cuuint64_t)SR_C * 2};
-  cuuint32_t box[2] = {(cuuint32_t)SR_C, (cuuint32_t)p.ocols};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = CUDA_SUCCESS;
+  for (int which = 0; which < 2 && r == CUDA_SUCCESS; ++which) {   // a warp's 32 pixels; the last warp's remainder of the row
+    const int tail = p.ocols % 32 ? p.ocols % 32 : 32;
+    cuuint32_t box[2] = {(cuuint32_t)SR_C, (cuuint32_t)(which == 0 ? 32 : tail)};
+    r = fn(which == 0 ? &tm : &tm_tail, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   if (r != CUDA_SUCCESS) {
     if (err) { char b[128]; snprintf(b, sizeof b, "stem output tensor map encode failed (CUresult %d)", (int)r); *err = b; }
     return cudaErrorInvalidValue;
@@ -322,8 +332,8 @@ cudaError_t launch_stem_rows(bf16* out, const StemArgs& a, const __half* wq_dev,
     if (e == cudaSuccess) e = ensure_dyn_smem((const void*)stem_rows_kernel<false>, 75 * 1024);
     if (e != cudaSuccess) return e;
   }
-  if (act != MNV1_ACT_NONE) return launch_pdl(stem_rows_kernel<true>, dim3((unsigned)grid), dim3(SR_THREADS), smem, st, tm, p);
-  return launch_pdl(stem_rows_kernel<false>, dim3((unsigned)grid), dim3(SR_THREADS), smem, st, tm, p);
+  if (act != MNV1_ACT_NONE) return launch_pdl(stem_rows_kernel<true>, dim3((unsigned)grid), dim3(SR_THREADS), smem, st, tm, tm_tail, p);
+  return launch_pdl(stem_rows_kernel<false>, dim3((unsigned)grid), dim3(SR_THREADS), smem, st, tm, tm_tail, p);
 }
 
 }  // namespace mnv1
