@@ -215,7 +215,7 @@ struct TimedLaunch {  // brackets one per-layer launch with the event pair (Mobi
 
 extern "C" {
 
-const char* mnv1_version(void) { return "mnv1-b200 0.1 (sm_100a)"; }
+const char* mnv1_version(void) { return "mnv1-b200 0.2 (sm_100a)"; }
 
 const char* mnv1_last_error(const mnv1_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
