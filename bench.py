@@ -90,7 +90,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-def launch_rows(layers, cum_ms, kernel_of, n, peaks):
+def launch_rows(layers, cum_ms, kernel_of, n, peaks, esz=2):
     """One row per LAUNCH of the captured graph.  cum_ms[k-1] is the median replay time of the graph of layers
     1..k (mnv1_profile_prefixes; -1 where no launch ends), so a launch's time is the difference of two
     consecutive boundaries and the rows add up to the whole step.  Algorithmic bytes:
@@ -106,9 +106,9 @@ def launch_rows(layers, cum_ms, kernel_of, n, peaks):
         t_ms = float(cum_ms[k - 1]) - prev
         prev, first = float(cum_ms[k - 1]), k
         Lin, Lout = group[0], group[-1]
-        in_b = Lin.in_elems * (1 if Lin.kind == STEM else 2)
-        out_b = Lout.out_elems * (4 if Lout.kind in (POOL, FC) else 2)
-        wbytes = sum(L.w_cnt * (4 if L.kind in (STEM, DEPTHWISE) else 2) for L in group)
+        in_b = Lin.in_elems * (1 if Lin.kind == STEM else esz)
+        out_b = Lout.out_elems * ((4 if Lout.kind in (POOL, FC) else 2) if esz == 2 else esz)
+        wbytes = sum(L.w_cnt * ((4 if L.kind in (STEM, DEPTHWISE) else 2) if esz == 2 else esz) for L in group)
         flops = sum(2.0 * L.macs * n for L in group)
         tc_flops = sum(2.0 * L.macs * n for L in group if L.kind == POINTWISE)
         kinds = [["stem", "dw", "pw", "pool", "fc"][L.kind] for L in group]
@@ -234,10 +234,18 @@ def integer_mode_throughput(mn, synth, dev_index, batch=256, steps=10):
         c.forward_device(img.data_ptr(), batch, lg.data_ptr(), t1.data_ptr(), p1.data_ptr())
     c.sync()
     dt = time.perf_counter() - t0
+    # per-launch times inside the graph and their HBM roofline at one byte per element (no measured int8 tensor peak on
+    # this pool: the pointwise rows are judged against HBM only)
+    peaks = load_peaks()
+    cum = c.profile_prefixes(img.data_ptr(), batch, iters=11)
+    names = kernel_names(c, mn, img.data_ptr(), batch, [k for k in range(1, 30) if cum[k - 1] >= 0])
+    rows = launch_rows(LAYERS, cum, names, batch, {"hbm_gbs": peaks["hbm_gbs"], "bf16_tflops": 1e9}, esz=1)
+    per = [{"layer": r["layer"], "kernel": r["kernel"], "us": r["us"], "hbm_roof_us": r["roof_us"], "frac_of_hbm_roofline": r["frac"]}
+           for r in rows]
     c.close()
     return {"batch": batch, "images_per_s": round(batch * steps / dt, 1), "ms_per_step": round(dt / steps * 1e3, 3),
             "arithmetic": "u8 activations x s8 filters -> s32 -> ReLU -> >> s -> saturating u8 store",
-            "timing": f"wall clock around {steps} graph replays after 3 warm-ups"}
+            "timing": f"wall clock around {steps} graph replays after 3 warm-ups", "per_launch": per}
 
 
 def h2d_ceiling(ctx, torch, dev, nbytes, world, dist):

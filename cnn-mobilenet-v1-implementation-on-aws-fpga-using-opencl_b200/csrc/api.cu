@@ -494,9 +494,11 @@ static int create_filter_u8(mnv1_ctx* ctx, mnv1_filter* f, const float* w, const
     for (int o = 0; o < cout; ++o)
       for (int t = 0; t < 27; ++t)
         packed[(size_t)o * 7 + (t >> 2)] |= (int)((uint32_t)(uint8_t)(int8_t)(int)w[(size_t)o * 27 + t] << (8 * (t & 3)));
-  } else if (f->kind == MNV1_DEPTHWISE) {    // [C][3][3] -> [9][C]
+  } else if (f->kind == MNV1_DEPTHWISE) {    // [C][3][3] -> [C][3] words (w[ty][0], w[ty][1], w[ty][2], 0): one DP4A per tap row
+    packed.assign((size_t)cout * 3, 0);
     for (int c = 0; c < cout; ++c)
-      for (int t = 0; t < 9; ++t) q[(size_t)t * cout + c] = (int8_t)(int)w[(size_t)c * 9 + t];
+      for (int t = 0; t < 9; ++t)
+        packed[(size_t)c * 3 + t / 3] |= (int)((uint32_t)(uint8_t)(int8_t)(int)w[(size_t)c * 9 + t] << (8 * (t % 3)));
   } else {
     for (size_t i = 0; i < cnt; ++i) q[i] = (int8_t)(int)w[i];                 // [Cout][Cin]: the K-major B operand as is
   }
@@ -671,7 +673,7 @@ static cudaError_t run_pointwise(mnv1_ctx* ctx, void* out, const void* in, const
   if (ctx->dtype == MNV1_U8) {
     ctx->last_kernel = "pointwise_i8_kernel";
     ctx->err.clear();
-    return mnv1::launch_pointwise_i8((uint8_t*)out, (const uint8_t*)in, f, m, f->cin, f->cout, ctx->u8_wrap, ctx->stream, &ctx->err);
+    return mnv1::launch_pointwise_i8((uint8_t*)out, (const uint8_t*)in, f, m, f->cin, f->cout, ctx->u8_wrap, ctx->num_sms, ctx->stream, &ctx->err);
   }
   if (ctx->dtype == MNV1_BF16 && f->has_tmap && !force_simt) {
     ctx->err.clear();
@@ -1034,7 +1036,7 @@ static cudaError_t enqueue_layers(mnv1_ctx* ctx, const uint8_t* d_img, int n, in
           uint8_t* logits8 = (uint8_t*)ctx->d_pooled + (size_t)ctx->plan_batch * 4096 + (size_t)ctx->plan_batch * 1024;
           ctx->err.clear();
           ctx->launches++; ctx->last_kernel = "pointwise_i8_kernel";
-          e = mnv1::launch_pointwise_i8(logits8, (const uint8_t*)cur, f, n, 1024, MNV1_NUM_CLASSES, ctx->u8_wrap, ctx->stream, &ctx->err);
+          e = mnv1::launch_pointwise_i8(logits8, (const uint8_t*)cur, f, n, 1024, MNV1_NUM_CLASSES, ctx->u8_wrap, ctx->num_sms, ctx->stream, &ctx->err);
           if (e == cudaSuccess) { e = mnv1::launch_u8_to_f32(d_logits, logits8, (long)n * MNV1_NUM_CLASSES, ctx->stream); ctx->launches++; }
           if (e == cudaSuccess && (d_top1 || d_prob)) {
             e = mnv1::launch_softmax(d_logits, n, MNV1_NUM_CLASSES, nullptr, d_top1, d_prob, ctx->stream);

@@ -201,7 +201,7 @@ cudaError_t launch_synth_images(uint8_t* out, long first_byte, long nbytes, uint
                                 cudaStream_t st);
 // ---- integer contexts (int8.cu): u8 activations x s8 filters -> s32 -> u8
 cudaError_t launch_pointwise_i8(uint8_t* out, const uint8_t* in, const mnv1_filter* f, long m, int k, int cout, int wrap,
-                                cudaStream_t st, std::string* err);
+                                int num_sms, cudaStream_t st, std::string* err);
 cudaError_t launch_depthwise_u8(uint8_t* out, const uint8_t* in, const mnv1_filter* f, int n, int rows, int cols, int stride,
                                 int c, int pad_lo, int wrap, cudaStream_t st);
 cudaError_t launch_stem_u8(uint8_t* out, const StemArgs& a, const mnv1_filter* f, int wrap, cudaStream_t st);

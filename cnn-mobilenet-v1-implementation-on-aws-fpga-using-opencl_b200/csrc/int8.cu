@@ -35,6 +35,18 @@ __device__ __forceinline__ int dp4a_u8s8(uint32_t a, int b, int c) {
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+// bytes (sat_u8(a), sat_u8(b), sat_u8(c), sat_u8(d)), a in the low byte: two cvt.pack.sat.u8.s32
+__device__ __forceinline__ uint32_t pack4_sat_u8(int a, int b, int c, int d) {
+  uint32_t hi, r;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+  return r;
+}
 __device__ __forceinline__ int finish(int acc, int bias, int relu, int rshift) {
   int v = acc + bias;
   if (relu) v = max(v, 0);
@@ -42,7 +54,7 @@ __device__ __forceinline__ int finish(int acc, int bias, int relu, int rshift) {
 }
 
 // ------------------------------------------------------------------------------------------ pointwise / FC
-constexpr int I8_BM = 128, I8_BK = 128, I8_STAGES = 4, I8_THREADS = 192;
+constexpr int I8_BM = 128, I8_STAGES = 4, I8_THREADS = 192;
 
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -67,29 +79,51 @@ struct I8Params {
   int K, Cout, relu, rshift, wrap;
 };
 
-// out[M][Cout] = store_u8(finish(in[M][K] . w[Cout][K]^T)).  One CTA per (128-row tile, BN-column tile):
-// warp 0 = TMA producer (4-stage ring of [128 x 128 B] A and [BN x 128 B] B tiles; rows / columns / K past
-// the tensor are zero-filled by the TMA unit), warp 1 = TMEM allocator + single-thread MMA issuer
-// (UMMA 128 x BN x 32, u8 x s8 -> s32), warps 2-5 = epilogue (tcgen05.ld of their 32 lanes, integer finish,
-// 4 bytes per word, 128-bit stores).
-template <int BN>
+// out[M][Cout] = store_u8(finish(in[M][K] . w[Cout][K]^T)).  Persistent CTAs loop over (128-row tile, BN-column tile)
+// units (n-tile innermost, so the A rows of a unit are re-read from L2):
+//   warp 0   TMA producer: 4-stage ring of [128 x 128 B] A and [BN x 128 B] B tiles, running ahead across units; rows /
+//            columns / K past the tensor are zero-filled by the TMA unit
+//   warp 1   TMEM allocator + single-thread MMA issuer (UMMA 128 x BN x 32, u8 x s8 -> s32) into TWO accumulator stages,
+//            so the epilogue of unit i overlaps the MMAs of unit i+1
+//   warps 2-5 epilogue: tcgen05.ld of their 32 lanes, integer finish, 4 bytes per word, 128-bit stores
+// KB = bytes (= u8 elements) of K per k-block and shared-memory row: 128 with the 128B swizzle, or — for the first layers,
+// whose whole contraction is 32 or 64 channels — 64 / 32 with the matching narrower swizzle, so that no zero-filled
+// columns are staged and multiplied (a [128 x 128 B] box over a 32-byte-wide tensor cost 3.6 k cycles per tile).
+template <int KB> __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr) {
+  constexpr uint64_t layout = KB == 128 ? 2 : KB == 64 ? 4 : 6;            // SWIZZLE_128B / _64B / _32B
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((8 * KB) >> 4) << 32;                                      // SBO: 8 rows
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+template <int BN, int KB>
 __global__ void __launch_bounds__(I8_THREADS) pointwise_i8_kernel(const __grid_constant__ CUtensorMap tmap_a,
                                                                   const __grid_constant__ CUtensorMap tmap_b,
                                                                   const I8Params p) {
+  constexpr int I8_BK = KB;
   constexpr uint32_t A_BYTES = I8_BM * I8_BK, B_BYTES = BN * I8_BK, STAGE = A_BYTES + B_BYTES;
-  constexpr uint32_t TM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t ACC = BN < 32 ? 32 : BN, TM_COLS = 2 * ACC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem + I8_STAGES * STAGE;
-  const uint32_t full = bars, empty = bars + 8u * I8_STAGES, tm_full = empty + 8u * I8_STAGES, tmem_slot = tm_full + 8;
+  const uint32_t full = bars, empty = bars + 8u * I8_STAGES, tm_full = empty + 8u * I8_STAGES, tm_empty = tm_full + 16, tmem_slot = tm_empty + 16;
+  const uint32_t sBias = tmem_slot + 16;                    // [n_tiles * BN] s32, zero past Cout: the epilogue reads it with broadcast LDS.128
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_idx = blockIdx.x * I8_BM, n_idx = blockIdx.y * BN;
   const int num_kb = (p.K + I8_BK - 1) / I8_BK;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  const long units = ((p.M + I8_BM - 1) / I8_BM) * n_tiles;
+  if (p.bias) {
+    int* sb = reinterpret_cast<int*>(smem_raw + (sBias - smem_u32(smem_raw)));
+    for (int i = threadIdx.x; i < n_tiles * BN; i += I8_THREADS) sb[i] = i < p.Cout ? __ldg(p.bias + i) : 0;
+  }
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     for (int s = 0; s < I8_STAGES; ++s) { mbar_init(full + 8u * s, 1); mbar_init(empty + 8u * s, 1); }
-    mbar_init(tm_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tm_full + 8u * a, 1); mbar_init(tm_empty + 8u * a, 4); }
     mbar_init_fence();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
@@ -98,68 +132,113 @@ __global__ void __launch_bounds__(I8_THREADS) pointwise_i8_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = lds32(tmem_slot);
 
+  // A filter that is a single (n-tile, k-block) — the first layers — is loaded ONCE per CTA, into stage 0's B slot, and
+  // every MMA reads it from there; the ring then carries A only (one TMA
+  // issue per tile instead of two: a thread starts a bulk copy every ~380 cycles).
+  const bool resident_b = n_tiles == 1 && num_kb == 1;
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % I8_STAGES;
-        mbar_wait(empty + 8u * s, ((kb / I8_STAGES) & 1) ^ 1u);
-        mbar_expect_tx(full + 8u * s, STAGE);
-        tma_load_2d(smem + s * STAGE, &tmap_a, full + 8u * s, kb * I8_BK, m_idx);
-        tma_load_2d(smem + s * STAGE + A_BYTES, &tmap_b, full + 8u * s, kb * I8_BK, n_idx);
+      int s = 0; uint32_t ph = 0;
+      bool first = true;
+      for (long u = blockIdx.x; u < units; u += gridDim.x) {
+        const int m_idx = (int)(u / n_tiles) * I8_BM, n_idx = (int)(u % n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty + 8u * s, ph ^ 1u);
+          const bool load_b = !resident_b || first;
+          mbar_expect_tx(full + 8u * s, load_b ? STAGE : A_BYTES);
+          tma_load_2d(smem + s * STAGE, &tmap_a, full + 8u * s, kb * I8_BK, m_idx);
+          if (load_b) tma_load_2d(smem + (resident_b ? 0u : (uint32_t)s * STAGE) + A_BYTES, &tmap_b, full + 8u * s, kb * I8_BK, n_idx);
+          first = false;
+          if (++s == I8_STAGES) { s = 0; ph ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_u8s8_m128(BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % I8_STAGES;
-        mbar_wait(full + 8u * s, (kb / I8_STAGES) & 1);
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (long u = blockIdx.x; u < units; u += gridDim.x) {
+        mbar_wait(tm_empty + 8u * as, aph ^ 1u);          // the epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint64_t da = umma_desc_sw128(smem + s * STAGE), db = umma_desc_sw128(smem + s * STAGE + A_BYTES);
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * ACC;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full + 8u * s, ph);
+          tc_fence_after();
+          const uint64_t da = umma_desc_kmajor<KB>(smem + s * STAGE);
+          const uint64_t db = umma_desc_kmajor<KB>(smem + (resident_b ? 0u : (uint32_t)s * STAGE) + A_BYTES);
 #pragma unroll
-        for (int k = 0; k < I8_BK / 32; ++k) umma_i8(tmem_base, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
-        umma_commit(empty + 8u * s);
+          for (int k = 0; k < I8_BK / 32; ++k) umma_i8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
+          umma_commit(empty + 8u * s);
+          if (++s == I8_STAGES) { s = 0; ph ^= 1u; }
+        }
+        umma_commit(tm_full + 8u * as);
+        if (++as == 2) { as = 0; aph ^= 1u; }
       }
-      umma_commit(tm_full);
     }
   } else {
     const int quarter = warp & 3;
-    const long row = (long)m_idx + quarter * 32 + lane;
-    mbar_wait(tm_full, 0);
-    tc_fence_after();
-    const bool vec = (p.Cout & 15) == 0;
+    const bool vec = (p.Cout & 31) == 0;                    // 32-byte rows pieces: one 256-bit store = one full sector
+    int as = 0; uint32_t aph = 0;
+    for (long u = blockIdx.x; u < units; u += gridDim.x) {
+      const int m_idx = (int)(u / n_tiles) * I8_BM, n_idx = (int)(u % n_tiles) * BN;
+      const long row = (long)m_idx + quarter * 32 + lane;
+      mbar_wait(tm_full + 8u * as, aph);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      const int col0 = n_idx + c0;
-      uint32_t q[8];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * ACC + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const int col0 = n_idx + c0;
+        int x[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t w = 0;
+        for (int j = 0; j < 32; ++j) x[j] = (int)v[j];
+        if (p.bias) {                                         // uniform; staged in shared memory, zero past Cout
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int col = col0 + 4 * j + b;
-          const int bias = (p.bias && col < p.Cout) ? __ldg(p.bias + col) : 0;
-          w |= store_u8(finish((int)v[4 * j + b], bias, p.relu, p.rshift), p.wrap) << (8 * b);
+          for (int j = 0; j < 8; ++j) {
+            int4 b4;
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(b4.x), "=r"(b4.y), "=r"(b4.z), "=r"(b4.w) : "r"(sBias + (uint32_t)(col0 + 4 * j) * 4u));
+            x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+          }
         }
-        q[j] = w;
-      }
-      if (row < p.M) {
-        uint8_t* o = p.out + row * p.Cout + col0;
-        if (vec && col0 + 32 <= p.Cout) {
-          reinterpret_cast<uint4*>(o)[0] = make_uint4(q[0], q[1], q[2], q[3]);
-          reinterpret_cast<uint4*>(o)[1] = make_uint4(q[4], q[5], q[6], q[7]);
+        uint32_t q[8];
+        if (!p.wrap) {
+          // saturating store: sat_u8(x >> s) — the ReLU is implied (a negative value stays negative under the arithmetic
+          // shift and saturates to 0); two cvt.pack.sat per four bytes
+          if (p.rshift) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] >>= p.rshift;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) q[j] = pack4_sat_u8(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
         } else {
+          // kernel.cl's store: ReLU, shift, then the C conversion to unsigned char (low byte)
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < p.Cout) o[j] = (uint8_t)(q[j >> 2] >> (8 * (j & 3)));
+          for (int j = 0; j < 32; ++j) { if (p.relu) x[j] = max(x[j], 0); x[j] >>= p.rshift; }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            q[j] = prmt(prmt((uint32_t)x[4 * j], (uint32_t)x[4 * j + 1], 0x0040), prmt((uint32_t)x[4 * j + 2], (uint32_t)x[4 * j + 3], 0x0040), 0x5410);
+        }
+        if (row < p.M) {
+          uint8_t* o = p.out + row * p.Cout + col0;
+          if (vec && col0 + 32 <= p.Cout) {
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]),
+                         "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]) : "memory");
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.Cout) o[j] = (uint8_t)(q[j >> 2] >> (8 * (j & 3)));
+          }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tm_empty + 8u * as);
+      if (++as == 2) { as = 0; aph ^= 1u; }
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -167,65 +246,108 @@ __global__ void __launch_bounds__(I8_THREADS) pointwise_i8_kernel(const __grid_c
   }
 }
 
-cudaError_t encode_u8(CUtensorMap* map, const void* base, uint64_t rows, uint64_t k, uint32_t box_rows, std::string* err) {
+cudaError_t encode_u8(CUtensorMap* map, const void* base, uint64_t rows, uint64_t k, uint32_t box_rows, int kb, std::string* err) {
   EncodeTiledFn fn = tensor_map_encoder();
   if (!fn) { if (err) *err = "cuTensorMapEncodeTiled unavailable"; return cudaErrorNotSupported; }
   cuuint64_t gdim[2] = {k, rows};
   cuuint64_t gstride[1] = {k};
-  cuuint32_t box[2] = {(cuuint32_t)I8_BK, box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)kb, box_rows};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = kb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : kb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { if (err) *err = "pointwise_i8: tensor map encode failed"; return cudaErrorInvalidValue; }
   return cudaSuccess;
 }
 
-template <int BN>
-cudaError_t launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, const I8Params& p, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + BN * I8_BK) + 16 * I8_STAGES + 32;
-  cudaError_t e = ensure_dyn_smem((const void*)pointwise_i8_kernel<BN>, (int)smem);
+template <int BN, int KB>
+cudaError_t launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, const I8Params& p, int num_sms, cudaStream_t st) {
+  constexpr int I8_BK = KB;
+  const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + BN * I8_BK) + 16 * I8_STAGES + 64 + (size_t)((p.Cout + BN - 1) / BN) * BN * 4;
+  cudaError_t e = ensure_dyn_smem((const void*)pointwise_i8_kernel<BN, KB>, (int)smem);
   if (e != cudaSuccess) return e;
-  dim3 grid((unsigned)((p.M + I8_BM - 1) / I8_BM), (unsigned)((p.Cout + BN - 1) / BN));
-  pointwise_i8_kernel<BN><<<grid, I8_THREADS, smem, st>>>(ta, tb, p);
+  const long units = ((p.M + I8_BM - 1) / I8_BM) * ((p.Cout + BN - 1) / BN);
+  const long per_sm = (227 * 1024) / (long)smem < 1 ? 1 : (227 * 1024) / (long)smem;     // resident CTAs per SM (shared memory)
+  long grid = (long)num_sms * (per_sm > 4 ? 4 : per_sm);
+  if (grid > units) grid = units;
+  pointwise_i8_kernel<BN, KB><<<(unsigned)grid, I8_THREADS, smem, st>>>(ta, tb, p);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------ depthwise
-// NHWC u8.  A thread owns one output pixel x 4 channels (one 32-bit word): for every tap the input word
-// is masked to one byte at a time, so that dp4a's 4-way dot product degenerates to the single u8 x s8
-// product of that channel.  taps: [9][C] s8 (tap-major, like the bf16 path's [9][C] floats).
+// NHWC u8.  A thread owns 4 adjacent output pixels x 4 channels (one 32-bit word per pixel).  DP4A is a 4-way dot
+// product over the BYTES of a word, and a 3x3 depthwise tap row is a 3-way dot product over adjacent PIXELS of one
+// channel — so the thread transposes its input words (pixel-major: 4 channels of one pixel) into channel-major words
+// (4 adjacent pixels of one channel, PRMT), forms the 3-pixel window of every output with a funnel shift (the 4th byte
+// meets a zero tap) and spends ONE dp4a.u32.s32 per (output, tap row): 3 instead of 9 multiply-adds per output.
+// rows32: [C][3] words, word = (w[ty][0], w[ty][1], w[ty][2], 0) as s8 — built once per filter (api.cu).
+// 4 words (pixels p0..p3, bytes = channels) -> 4 words (channels, bytes = pixels p0..p3)
+__device__ __forceinline__ void transpose4(const uint32_t (&w)[4], uint32_t (&c)[4]) {
+  const uint32_t t0 = prmt(w[0], w[1], 0x5140), t1 = prmt(w[2], w[3], 0x5140);   // (a.b0 b.b0 a.b1 b.b1)
+  const uint32_t t2 = prmt(w[0], w[1], 0x7362), t3 = prmt(w[2], w[3], 0x7362);   // (a.b2 b.b2 a.b3 b.b3)
+  c[0] = prmt(t0, t1, 0x5410); c[1] = prmt(t0, t1, 0x7632);
+  c[2] = prmt(t2, t3, 0x5410); c[3] = prmt(t2, t3, 0x7632);
+}
+template <int S>
 __global__ void __launch_bounds__(256) depthwise_u8_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in,
-                                                           const int8_t* __restrict__ taps, const int* __restrict__ bias,
-                                                           int n, int H, int W, int C, int stride, int pad_lo, int relu,
-                                                           int rshift, int wrap) {
-  const int Ho = H / stride, Wo = W / stride, C4 = C >> 2;
-  const long total = (long)n * Ho * Wo * C4;
+                                                           const int* __restrict__ rows32, const int* __restrict__ bias,
+                                                           int n, int H, int W, int C, int pad_lo, int relu, int rshift,
+                                                           int wrap) {
+  constexpr int NPX = 3 * S + 3;              // input pixels a strip of 4 outputs needs: 6 (stride 1) or 9 (stride 2)
+  constexpr int NW = (NPX + 3) / 4;           // channel-major words per channel: 2 or 3
+  const int Ho = H / S, Wo = W / S, C4 = C >> 2, strips = (Wo + 3) >> 2;
+  const long total = (long)n * Ho * strips * C4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
     long r = i / C4;
-    const int x = (int)(r % Wo); r /= Wo;
+    const int strip = (int)(r % strips); r /= strips;
     const int y = (int)(r % Ho);
     const int img = (int)(r / Ho);
-    int acc[4] = {0, 0, 0, 0};
+    const int x0 = strip * 4;
+    int acc[4][4];                            // [channel][output pixel]
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0;
 #pragma unroll
     for (int ty = 0; ty < 3; ++ty) {
-      const int yy = y * stride + ty - pad_lo;
+      const int yy = y * S + ty - pad_lo;
+      if (yy < 0 || yy >= H) continue;                                      // zero padding: the row contributes nothing
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(in + ((long)img * H + yy) * W * C) + c4;
+      uint32_t px[NW * 4];
 #pragma unroll
-      for (int tx = 0; tx < 3; ++tx) {
-        const int xx = x * stride + tx - pad_lo;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;          // zero padding on every border
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(in + (((long)img * H + yy) * W + xx) * C) + c4);
-        const int t = __ldg(reinterpret_cast<const int*>(taps + (long)(ty * 3 + tx) * C) + c4);
+      for (int k = 0; k < NW * 4; ++k) {
+        const int xx = x0 * S + k - pad_lo;
+        px[k] = (k < NPX && xx >= 0 && xx < W) ? __ldg(row + (long)xx * C4) : 0u;
+      }
+      uint32_t ch[NW][4];                                                   // [group of 4 pixels][channel]
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[b] = dp4a_u8s8(v & (0xffu << (8 * b)), t, acc[b]);   // u8 x s8, one channel
+      for (int g = 0; g < NW; ++g) {
+        const uint32_t w4[4] = {px[4 * g], px[4 * g + 1], px[4 * g + 2], px[4 * g + 3]};
+        transpose4(w4, ch[g]);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int t = __ldg(rows32 + (long)(4 * c4 + b) * 3 + ty);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int start = j * S;                                          // first input pixel of output j's window
+          const uint32_t lo = ch[start >> 2][b], hi = ch[(start >> 2) + 1 < NW ? (start >> 2) + 1 : NW - 1][b];
+          const uint32_t win = (start & 3) ? __funnelshift_r(lo, hi, 8 * (start & 3)) : lo;
+          acc[b][j] = dp4a_u8s8(win, t, acc[b][j]);
+        }
       }
     }
-    uint32_t w = 0;
+    int bs[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b)
-      w |= store_u8(finish(acc[b], bias ? __ldg(bias + 4 * c4 + b) : 0, relu, rshift), wrap) << (8 * b);
-    reinterpret_cast<uint32_t*>(out + (((long)img * Ho + y) * Wo + x) * C)[c4] = w;
+    for (int b = 0; b < 4; ++b) bs[b] = bias ? __ldg(bias + 4 * c4 + b) : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (x0 + j >= Wo) break;
+      uint32_t w = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) w |= store_u8(finish(acc[b][j], bs[b], relu, rshift), wrap) << (8 * b);
+      reinterpret_cast<uint32_t*>(out + (((long)img * Ho + y) * Wo + x0 + j) * C)[c4] = w;
+    }
   }
 }
 
@@ -327,31 +449,47 @@ unsigned grid_for(long total, int block) {
 
 // ---------------------------------------------------------------------------------------------- launchers
 cudaError_t launch_pointwise_i8(uint8_t* out, const uint8_t* in, const mnv1_filter* f, long m, int k, int cout, int wrap,
-                                cudaStream_t st, std::string* err) {
+                                int num_sms, cudaStream_t st, std::string* err) {
   if (!f->w_s8 || k % 16 || k < 16) { if (err) *err = "pointwise (u8): Cin must be a multiple of 16"; return cudaErrorNotSupported; }
   if (m <= 0) return cudaSuccess;
   const int bn = cout >= 256 ? 256 : cout > 64 ? 128 : cout > 32 ? 64 : cout > 16 ? 32 : 16;
+  const int kb = k == 32 ? 32 : k == 64 ? 64 : 128;
   CUtensorMap ta, tb;
-  cudaError_t e = encode_u8(&ta, in, (uint64_t)m, (uint64_t)k, I8_BM, err);
-  if (e == cudaSuccess) e = encode_u8(&tb, f->w_s8, (uint64_t)cout, (uint64_t)k, (uint32_t)bn, err);
+  cudaError_t e = encode_u8(&ta, in, (uint64_t)m, (uint64_t)k, I8_BM, kb, err);
+  if (e == cudaSuccess) e = encode_u8(&tb, f->w_s8, (uint64_t)cout, (uint64_t)k, (uint32_t)bn, kb, err);
   if (e != cudaSuccess) return e;
   I8Params p{out, f->bias_i32, m, k, cout, f->act != MNV1_ACT_NONE ? 1 : 0, f->rshift, wrap};
+  if (kb == 32) {          // layer 3 of the schedule (32 -> 64)
+    if (bn == 64) return launch_i8<64, 32>(ta, tb, p, num_sms, st);
+    if (bn == 128) return launch_i8<128, 32>(ta, tb, p, num_sms, st);
+  } else if (kb == 64) {   // layer 5 (64 -> 128)
+    if (bn == 128) return launch_i8<128, 64>(ta, tb, p, num_sms, st);
+    if (bn == 64) return launch_i8<64, 64>(ta, tb, p, num_sms, st);
+  }
+  if (kb != 128) {         // other shapes with a narrow contraction: 128-byte boxes, zero-filled by the TMA unit
+    e = encode_u8(&ta, in, (uint64_t)m, (uint64_t)k, I8_BM, 128, err);
+    if (e == cudaSuccess) e = encode_u8(&tb, f->w_s8, (uint64_t)cout, (uint64_t)k, (uint32_t)bn, 128, err);
+    if (e != cudaSuccess) return e;
+  }
   switch (bn) {
-    case 256: return launch_i8<256>(ta, tb, p, st);
-    case 128: return launch_i8<128>(ta, tb, p, st);
-    case 64: return launch_i8<64>(ta, tb, p, st);
-    case 32: return launch_i8<32>(ta, tb, p, st);
-    default: return launch_i8<16>(ta, tb, p, st);
+    case 256: return launch_i8<256, 128>(ta, tb, p, num_sms, st);
+    case 128: return launch_i8<128, 128>(ta, tb, p, num_sms, st);
+    case 64: return launch_i8<64, 128>(ta, tb, p, num_sms, st);
+    case 32: return launch_i8<32, 128>(ta, tb, p, num_sms, st);
+    default: return launch_i8<16, 128>(ta, tb, p, num_sms, st);
   }
 }
 
 cudaError_t launch_depthwise_u8(uint8_t* out, const uint8_t* in, const mnv1_filter* f, int n, int rows, int cols, int stride,
                                 int c, int pad_lo, int wrap, cudaStream_t st) {
-  if (c % 4) return cudaErrorNotSupported;
+  if (c % 4 || !f->w_q32) return cudaErrorNotSupported;
   if (n <= 0) return cudaSuccess;
-  const long total = (long)n * (rows / stride) * (cols / stride) * (c / 4);
-  depthwise_u8_kernel<<<grid_for(total, 256), 256, 0, st>>>(out, in, f->w_s8, f->bias_i32, n, rows, cols, c, stride, pad_lo,
-                                                            f->act != MNV1_ACT_NONE ? 1 : 0, f->rshift, wrap);
+  const long total = (long)n * (rows / stride) * ((cols / stride + 3) / 4) * (c / 4);
+  const int relu = f->act != MNV1_ACT_NONE ? 1 : 0;
+  if (stride == 1)
+    depthwise_u8_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(out, in, f->w_q32, f->bias_i32, n, rows, cols, c, pad_lo, relu, f->rshift, wrap);
+  else
+    depthwise_u8_kernel<2><<<grid_for(total, 256), 256, 0, st>>>(out, in, f->w_q32, f->bias_i32, n, rows, cols, c, pad_lo, relu, f->rshift, wrap);
   return cudaGetLastError();
 }
 

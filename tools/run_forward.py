@@ -20,10 +20,21 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--dtype", default="bf16")
     a = ap.parse_args()
-    ctx = mn.Context(0, {"bf16": mn.BF16, "f32": mn.F32}[a.dtype])
+    ctx = mn.Context(0, {"bf16": mn.BF16, "f32": mn.F32, "u8": mn.U8}[a.dtype])
     ctx.set_pad_mode(mn.PAD_TFSAME)
-    ctx.set_input_transform(1 / 127.5, -1.0)
-    ctx.set_weights(synth.weights(), *synth.batchnorm(), mn.ACT_RELU6)
+    if a.dtype == "u8":      # the integer contexts: seeded s8 filters, a per-layer requantisation shift (bench.py's configs.u8)
+        import numpy as np
+        from mnv1_b200.layers import LAYERS, TOTAL_WEIGHTS, TOTAL_CHANNELS, DEPTHWISE, STEM, POOL
+        w = synth.kat_ints(99, TOTAL_WEIGHTS, -127, 127).astype(np.float32)
+        sc = np.ones(TOTAL_CHANNELS, np.float32)
+        for L in LAYERS:
+            if L.kind != POOL:
+                fan = 27 if L.kind == STEM else 9 if L.kind == DEPTHWISE else L.cin
+                sc[L.c_off:L.c_off + L.cout] = 2.0 ** -int(np.ceil(np.log2(np.sqrt(fan) * 74 * 1.2)))
+        ctx.set_weights(w, sc, np.zeros(TOTAL_CHANNELS, np.float32), mn.ACT_RELU)
+    else:
+        ctx.set_input_transform(1 / 127.5, -1.0)
+        ctx.set_weights(synth.weights(), *synth.batchnorm(), mn.ACT_RELU6)
     ctx.plan(a.n)
     img = torch.empty(a.n * 224 * 224 * 3, dtype=torch.uint8, device="cuda")
     lg = torch.empty(a.n, 1000, device="cuda"); t1 = torch.empty(a.n, dtype=torch.int32, device="cuda"); p1 = torch.empty(a.n, device="cuda")
