@@ -489,11 +489,15 @@ static int create_filter_u8(mnv1_ctx* ctx, mnv1_filter* f, const float* w, const
   }
   std::vector<int8_t> q(cnt);
   std::vector<int> packed;
-  if (f->kind == MNV1_CONVOLUTE) {           // [O][3][3][3] -> 7 words of 4 taps per filter (28th tap = 0)
-    packed.assign((size_t)cout * 7, 0);
+  if (f->kind == MNV1_CONVOLUTE) {           // [O][plane][ty][tx] -> 7 words of 4 taps per filter in the order an interleaved
+    packed.assign((size_t)cout * 7, 0);      // RGB row delivers the window bytes: k = 9 ty + 3 tx + plane (28th tap = 0)
     for (int o = 0; o < cout; ++o)
-      for (int t = 0; t < 27; ++t)
-        packed[(size_t)o * 7 + (t >> 2)] |= (int)((uint32_t)(uint8_t)(int8_t)(int)w[(size_t)o * 27 + t] << (8 * (t & 3)));
+      for (int pl = 0; pl < 3; ++pl)
+        for (int ty = 0; ty < 3; ++ty)
+          for (int tx = 0; tx < 3; ++tx) {
+            const int k = 9 * ty + 3 * tx + pl;
+            packed[(size_t)o * 7 + (k >> 2)] |= (int)((uint32_t)(uint8_t)(int8_t)(int)w[(size_t)o * 27 + pl * 9 + ty * 3 + tx] << (8 * (k & 3)));
+          }
   } else if (f->kind == MNV1_DEPTHWISE) {    // [C][3][3] -> [C][3] words (w[ty][0], w[ty][1], w[ty][2], 0): one DP4A per tap row
     packed.assign((size_t)cout * 3, 0);
     for (int c = 0; c < cout; ++c)

@@ -289,72 +289,111 @@ __device__ __forceinline__ void transpose4(const uint32_t (&w)[4], uint32_t (&c)
   c[0] = prmt(t0, t1, 0x5410); c[1] = prmt(t0, t1, 0x7632);
   c[2] = prmt(t2, t3, 0x5410); c[3] = prmt(t2, t3, 0x7632);
 }
+// The thread walks DOWN a band of RB output rows: every input row is loaded, transposed and windowed once and feeds the
+// (up to) three output rows it belongs to, whose accumulators live in a ring of 3 (stride 1) / 2 (stride 2) slots —
+// the row loop is fully unrolled, so the slots are compile-time registers.
 template <int S>
 __global__ void __launch_bounds__(256) depthwise_u8_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in,
                                                            const int* __restrict__ rows32, const int* __restrict__ bias,
                                                            int n, int H, int W, int C, int pad_lo, int relu, int rshift,
                                                            int wrap) {
+  constexpr int RB = 7;                       // output rows per thread (every map of the schedule is a multiple of 7 high)
+  constexpr int HR = (RB - 1) * S + 3;        // input rows of a band
+  constexpr int RING = S == 1 ? 3 : 2;
   constexpr int NPX = 3 * S + 3;              // input pixels a strip of 4 outputs needs: 6 (stride 1) or 9 (stride 2)
   constexpr int NW = (NPX + 3) / 4;           // channel-major words per channel: 2 or 3
-  const int Ho = H / S, Wo = W / S, C4 = C >> 2, strips = (Wo + 3) >> 2;
-  const long total = (long)n * Ho * strips * C4;
+  const int Ho = H / S, Wo = W / S, C4 = C >> 2, strips = (Wo + 3) >> 2, bands = (Ho + RB - 1) / RB;
+  const long total = (long)n * bands * strips * C4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i % C4);
     long r = i / C4;
     const int strip = (int)(r % strips); r /= strips;
-    const int y = (int)(r % Ho);
-    const int img = (int)(r / Ho);
-    const int x0 = strip * 4;
-    int acc[4][4];                            // [channel][output pixel]
+    const int band = (int)(r % bands);
+    const int img = (int)(r / bands);
+    const int x0 = strip * 4, y0 = band * RB;
+    int taps[4][3], bs[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0;
+    for (int b = 0; b < 4; ++b) {
 #pragma unroll
-    for (int ty = 0; ty < 3; ++ty) {
-      const int yy = y * S + ty - pad_lo;
-      if (yy < 0 || yy >= H) continue;                                      // zero padding: the row contributes nothing
-      const uint32_t* row = reinterpret_cast<const uint32_t*>(in + ((long)img * H + yy) * W * C) + c4;
-      uint32_t px[NW * 4];
+      for (int ty = 0; ty < 3; ++ty) taps[b][ty] = __ldg(rows32 + (long)(4 * c4 + b) * 3 + ty);
+      bs[b] = bias ? __ldg(bias + 4 * c4 + b) : 0;
+    }
+    int acc[RING][4][4];                      // [slot][channel][output pixel]
 #pragma unroll
-      for (int k = 0; k < NW * 4; ++k) {
-        const int xx = x0 * S + k - pad_lo;
-        px[k] = (k < NPX && xx >= 0 && xx < W) ? __ldg(row + (long)xx * C4) : 0u;
+    for (int q = 0; q < HR; ++q) {
+      if (q % S == 0 && q / S < RB) {         // output row q / S starts with this input row: fresh accumulators (+ bias)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[(q / S) % RING][b][j] = bs[b];
       }
-      uint32_t ch[NW][4];                                                   // [group of 4 pixels][channel]
+      const int yy = y0 * S + q - pad_lo;
+      if (yy >= 0 && yy < H) {                // a row outside the image is the zero padding: it contributes nothing
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(in + ((long)img * H + yy) * W * C) + c4;
+        uint32_t px[NW * 4];
 #pragma unroll
-      for (int g = 0; g < NW; ++g) {
-        const uint32_t w4[4] = {px[4 * g], px[4 * g + 1], px[4 * g + 2], px[4 * g + 3]};
-        transpose4(w4, ch[g]);
-      }
+        for (int k = 0; k < NW * 4; ++k) {
+          const int xx = x0 * S + k - pad_lo;
+          px[k] = (k < NPX && xx >= 0 && xx < W) ? __ldg(row + (long)xx * C4) : 0u;
+        }
+        uint32_t ch[NW][4];                   // [group of 4 pixels][channel]
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int t = __ldg(rows32 + (long)(4 * c4 + b) * 3 + ty);
+        for (int g = 0; g < NW; ++g) {
+          const uint32_t w4[4] = {px[4 * g], px[4 * g + 1], px[4 * g + 2], px[4 * g + 3]};
+          transpose4(w4, ch[g]);
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int start = j * S;                                          // first input pixel of output j's window
-          const uint32_t lo = ch[start >> 2][b], hi = ch[(start >> 2) + 1 < NW ? (start >> 2) + 1 : NW - 1][b];
-          const uint32_t win = (start & 3) ? __funnelshift_r(lo, hi, 8 * (start & 3)) : lo;
-          acc[b][j] = dp4a_u8s8(win, t, acc[b][j]);
+        for (int b = 0; b < 4; ++b) {
+          uint32_t win[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int start = j * S;          // first input pixel of output j's window
+            const uint32_t lo = ch[start >> 2][b], hi = ch[(start >> 2) + 1 < NW ? (start >> 2) + 1 : NW - 1][b];
+            win[j] = (start & 3) ? __funnelshift_r(lo, hi, 8 * (start & 3)) : lo;
+          }
+#pragma unroll
+          for (int ty = 0; ty < 3; ++ty) {    // input row q is tap row ty of output row (q - ty) / S
+            if (q - ty >= 0 && (q - ty) % S == 0 && (q - ty) / S < RB) {
+              const int slot = ((q - ty) / S) % RING;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[slot][b][j] = dp4a_u8s8(win[j], taps[b][ty], acc[slot][b][j]);
+            }
+          }
         }
       }
-    }
-    int bs[4];
+      if (q - 2 >= 0 && (q - 2) % S == 0 && (q - 2) / S < RB) {     // output row (q - 2) / S is complete
+        const int o = (q - 2) / S, slot = o % RING, y = y0 + o;
+        if (y < Ho) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) bs[b] = bias ? __ldg(bias + 4 * c4 + b) : 0;
+          for (int j = 0; j < 4; ++j) {
+            if (x0 + j >= Wo) break;
+            int v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (x0 + j >= Wo) break;
-      uint32_t w = 0;
+            for (int b = 0; b < 4; ++b) v[b] = acc[slot][b][j];
+            uint32_t w;
+            if (!wrap) {                      // sat_u8(v >> s): the ReLU is implied by the saturation at 0
 #pragma unroll
-      for (int b = 0; b < 4; ++b) w |= store_u8(finish(acc[b][j], bs[b], relu, rshift), wrap) << (8 * b);
-      reinterpret_cast<uint32_t*>(out + (((long)img * Ho + y) * Wo + x0 + j) * C)[c4] = w;
+              for (int b = 0; b < 4; ++b) v[b] >>= rshift;
+              w = pack4_sat_u8(v[0], v[1], v[2], v[3]);
+            } else {                          // kernel.cl: ReLU, then the C conversion to unsigned char
+#pragma unroll
+              for (int b = 0; b < 4; ++b) { if (relu) v[b] = max(v[b], 0); v[b] >>= rshift; }
+              w = prmt(prmt((uint32_t)v[0], (uint32_t)v[1], 0x0040), prmt((uint32_t)v[2], (uint32_t)v[3], 0x0040), 0x5410);
+            }
+            reinterpret_cast<uint32_t*>(out + (((long)img * Ho + y) * Wo + x0 + j) * C)[c4] = w;
+          }
+        }
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------ stem
-// A thread owns one output pixel and all 32 filters.  Its 27 input bytes (R taps, G taps, B taps in the
-// `findex` order of kernel.cl:15-51) are packed into 7 words; every filter's 27 s8 values are packed the same
-// way, so one filter costs 7 DP4A.  wq: [32][7] words in shared memory.
+// A thread owns one output pixel and all 32 filters.  Its 27 input bytes are packed into 7 words in the order
+// k = 9*ty + 3*tx + plane — the order in which an interleaved RGB row delivers them: the 9 window bytes of a row are
+// contiguous, so each row costs three aligned 32-bit loads and a funnel shift instead of nine byte loads.  Every filter's
+// 27 s8 values are packed in the same order (api.cu), so one filter costs 7 DP4A.  Planar inputs (the reference's
+// three-plane calling convention) place their bytes in the same order one at a time.  wq: [32][7] words.
 __global__ void __launch_bounds__(128) stem_u8_kernel(uint8_t* __restrict__ out, const StemArgs a, const int* __restrict__ wq,
                                                       const int* __restrict__ bias, int relu, int rshift, int wrap) {
   __shared__ int s_w[32 * 7];
@@ -364,38 +403,84 @@ __global__ void __launch_bounds__(128) stem_u8_kernel(uint8_t* __restrict__ out,
   __syncthreads();
   const int Ho = a.rows / a.stride, Wo = a.cols / a.stride;
   const long total = (long)a.n * Ho * Wo;
+  const bool interleaved = a.pix_stride == 3 && a.g == a.r + 1 && a.b == a.r + 2 && (a.cols * 3) % 4 == 0 && a.img_stride % 4 == 0 &&
+                           (reinterpret_cast<uintptr_t>(a.r) & 3) == 0;
+  const int rowbytes = a.cols * 3;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int x = (int)(i % Wo);
     const int y = (int)((i / Wo) % Ho);
     const int img = (int)(i / ((long)Wo * Ho));
-    uint32_t pk[7] = {0, 0, 0, 0, 0, 0, 0};
-    const uint8_t* planes[3] = {a.r + (long)img * a.img_stride, a.g + (long)img * a.img_stride, a.b + (long)img * a.img_stride};
+    uint32_t rw[3][3];                                   // the 9 window bytes of each row: two words + one byte
+    if (interleaved) {
+      const int start = (x * a.stride - a.pad_lo) * 3;   // may be negative (left padding) or run past the row (right padding)
+      const int al = start & ~3, sh = 8 * (start & 3);
 #pragma unroll
-    for (int pl = 0; pl < 3; ++pl)
+      for (int ty = 0; ty < 3; ++ty) {
+        const int yy = y * a.stride + ty - a.pad_lo;
+        uint32_t w[3] = {0u, 0u, 0u};
+        if (yy >= 0 && yy < a.rows) {
+          const uint8_t* row = a.r + (long)img * a.img_stride + (long)yy * rowbytes;
 #pragma unroll
-      for (int ty = 0; ty < 3; ++ty)
-#pragma unroll
-        for (int tx = 0; tx < 3; ++tx) {
-          const int yy = y * a.stride + ty - a.pad_lo, xx = x * a.stride + tx - a.pad_lo;
-          uint32_t v = 0;
-          if (yy >= 0 && yy < a.rows && xx >= 0 && xx < a.cols) v = planes[pl][((long)yy * a.cols + xx) * a.pix_stride];
-          const int t = pl * 9 + ty * 3 + tx;
-          pk[t >> 2] |= v << (8 * (t & 3));
+          for (int k = 0; k < 3; ++k) {
+            const int off = al + 4 * k;
+            if (off >= 0 && off + 4 <= rowbytes) w[k] = __ldg(reinterpret_cast<const uint32_t*>(row + off));
+          }
         }
+        rw[ty][0] = __funnelshift_r(w[0], w[1], sh);
+        rw[ty][1] = __funnelshift_r(w[1], w[2], sh);
+        rw[ty][2] = (w[2] >> sh) & 0xffu;
+      }
+    } else {
+      const uint8_t* planes[3] = {a.r + (long)img * a.img_stride, a.g + (long)img * a.img_stride, a.b + (long)img * a.img_stride};
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) {
+        rw[ty][0] = rw[ty][1] = rw[ty][2] = 0u;
+#pragma unroll
+        for (int tx = 0; tx < 3; ++tx)
+#pragma unroll
+          for (int pl = 0; pl < 3; ++pl) {
+            const int yy = y * a.stride + ty - a.pad_lo, xx = x * a.stride + tx - a.pad_lo;
+            uint32_t v = 0;
+            if (yy >= 0 && yy < a.rows && xx >= 0 && xx < a.cols) v = planes[pl][((long)yy * a.cols + xx) * a.pix_stride];
+            const int k = 3 * tx + pl;
+            rw[ty][k >> 2] |= v << (8 * (k & 3));
+          }
+      }
+    }
+    // 27 bytes -> 7 words: row 0 at byte 0, row 1 at byte 9, row 2 at byte 18
+    uint32_t pk[7];
+    pk[0] = rw[0][0];
+    pk[1] = rw[0][1];
+    pk[2] = rw[0][2] | (rw[1][0] << 8);                                      // r0[8], r1[0..2]
+    pk[3] = __funnelshift_r(rw[1][0], rw[1][1], 24);                         // r1[3..6]
+    pk[4] = (rw[1][1] >> 24) | (rw[1][2] << 8) | (rw[2][0] << 16);           // r1[7], r1[8], r2[0..1]
+    pk[5] = __funnelshift_r(rw[2][0], rw[2][1], 16);                         // r2[2..5]
+    pk[6] = (rw[2][1] >> 16) | (rw[2][2] << 16);                             // r2[6..7], r2[8], 0
     uint32_t* o = reinterpret_cast<uint32_t*>(out + i * 32);
+    uint32_t q[8];
 #pragma unroll
     for (int f4 = 0; f4 < 8; ++f4) {
-      uint32_t w = 0;
+      int v[4];
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int f = 4 * f4 + b;
-        int acc = 0;
+        int acc = s_b[f];
 #pragma unroll
         for (int k = 0; k < 7; ++k) acc = dp4a_u8s8(pk[k], s_w[f * 7 + k], acc);
-        w |= store_u8(finish(acc, s_b[f], relu, rshift), wrap) << (8 * b);
+        v[b] = acc;
       }
-      o[f4] = w;
+      if (!wrap) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) v[b] >>= rshift;
+        q[f4] = pack4_sat_u8(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) { if (relu) v[b] = max(v[b], 0); v[b] >>= rshift; }
+        q[f4] = prmt(prmt((uint32_t)v[0], (uint32_t)v[1], 0x0040), prmt((uint32_t)v[2], (uint32_t)v[3], 0x0040), 0x5410);
+      }
     }
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]),
+                 "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]) : "memory");
   }
 }
 
@@ -452,7 +537,9 @@ cudaError_t launch_pointwise_i8(uint8_t* out, const uint8_t* in, const mnv1_filt
                                 int num_sms, cudaStream_t st, std::string* err) {
   if (!f->w_s8 || k % 16 || k < 16) { if (err) *err = "pointwise (u8): Cin must be a multiple of 16"; return cudaErrorNotSupported; }
   if (m <= 0) return cudaSuccess;
-  const int bn = cout >= 256 ? 256 : cout > 64 ? 128 : cout > 32 ? 64 : cout > 16 ? 32 : 16;
+  int bn = cout >= 256 ? 256 : cout > 64 ? 128 : cout > 32 ? 64 : cout > 16 ? 32 : 16;
+  // few rows (the FC layer: M = batch): narrower column tiles spread the contraction over more SMs
+  if (bn > 64 && ((m + I8_BM - 1) / I8_BM) * ((cout + bn - 1) / bn) * 2 < num_sms) bn = 64;
   const int kb = k == 32 ? 32 : k == 64 ? 64 : 128;
   CUtensorMap ta, tb;
   cudaError_t e = encode_u8(&ta, in, (uint64_t)m, (uint64_t)k, I8_BM, kb, err);
@@ -484,7 +571,7 @@ cudaError_t launch_depthwise_u8(uint8_t* out, const uint8_t* in, const mnv1_filt
                                 int c, int pad_lo, int wrap, cudaStream_t st) {
   if (c % 4 || !f->w_q32) return cudaErrorNotSupported;
   if (n <= 0) return cudaSuccess;
-  const long total = (long)n * (rows / stride) * ((cols / stride + 3) / 4) * (c / 4);
+  const long total = (long)n * ((rows / stride + 6) / 7) * ((cols / stride + 3) / 4) * (c / 4);
   const int relu = f->act != MNV1_ACT_NONE ? 1 : 0;
   if (stride == 1)
     depthwise_u8_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(out, in, f->w_q32, f->bias_i32, n, rows, cols, c, pad_lo, relu, f->rshift, wrap);
