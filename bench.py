@@ -249,14 +249,31 @@ def integer_mode_throughput(mn, synth, dev_index, batch=256, steps=10):
 
 
 def h2d_ceiling(ctx, torch, dev, nbytes, world, dist):
-    """What a plain pinned cudaMemcpyAsync loop reaches on this box with every rank copying at once
-    (mnv1_h2d_probe: 20 copies of one batch back to back, CUDA events): the ceiling of the e2e number."""
-    if world > 1:
-        dist.barrier()
-    g = torch.tensor([ctx.h2d_probe(nbytes, 21)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(g, op=dist.ReduceOp.SUM)     # ranks copy concurrently: the box's aggregate
-    return float(g.item())
+    """What plain pinned cudaMemcpyAsync copies of one batch reach on this box with every rank copying at once
+    (mnv1_h2d_probe_*: back-to-back copies over three rotating source buffers, CUDA events): the ceiling of the e2e
+    number.  Every rank allocates first, a barrier starts the copies together; a second pass gives each rank a copy count
+    in proportion to its first rate so that all ranks copy until the end — otherwise the ranks with the fast links finish
+    early and the slow ones report a rate they never see in the steady state.  Returns (sum GB/s, per-rank GB/s)."""
+    def gathered(x):
+        g = torch.tensor([x], dtype=torch.float64, device=dev)
+        per_rank = [g.clone() for _ in range(world)]
+        if world > 1:
+            dist.all_gather(per_rank, g)
+        return [float(t.item()) for t in per_rank]
+
+    probe = ctx.h2d_probe_open(nbytes)
+    try:
+        if world > 1:
+            dist.barrier()
+        first = gathered(ctx.h2d_probe_run(probe, 12))
+        mine = first[dist.get_rank() if world > 1 else 0]
+        reps = max(4, int(30 * mine / max(first) + 0.5))
+        if world > 1:
+            dist.barrier()
+        rates = [round(x, 1) for x in gathered(ctx.h2d_probe_run(probe, reps))]
+    finally:
+        ctx.h2d_probe_close(probe)
+    return float(sum(rates)), rates
 
 
 def host_cpus():
@@ -441,9 +458,75 @@ def run_ours(args):
             reps.append(time.perf_counter() - t0)
         e2e_s = sorted(reps)[1]
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        e2e_ranks = [te.clone() for _ in range(world)]
         if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e_value = world * batch * ke / float(te.item())
+            dist.all_gather(e2e_ranks, te)
+        e2e_ranks = [float(t.item()) for t in e2e_ranks]
+        e2e_value = world * batch * ke / max(e2e_ranks)
+        # ---- N > 1: the box does not feed its GPUs evenly (8 x B200 here: 25 GB/s to four of them, 38 GB/s to the other
+        # four when all copy at once), and with equal shards every step waits for the slowest link.  The same global
+        # batch cut in proportion to each rank's measured concurrent H2D rate (mnv1_dp_shard_weighted; what
+        # mnv1_dp_calibrate does inside one process) lets the uploads of a step finish together.
+        e2e_equal_value, e2e_equal_ranks, shard_info = None, None, None
+        if world > 1:
+            def weighted_e2e(weights, repetitions):
+                """ke pipelined steps with this rank's share of the global batch; per-rank seconds (median) and the shares"""
+                first, cnt = mn.dp_shard_weighted(world * batch, rank, world, weights)
+                counts = [mn.dp_shard_weighted(world * batch, r, world, weights)[1] for r in range(world)]
+                if cnt > getattr(ctx, "planned_batch", 0):
+                    ctx.plan(cnt)
+                if ctx.gather_active():
+                    ctx.gather_set_rows(first, cnt)
+                hp_imgs = [torch.empty(cnt * IMG_BYTES, dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
+                for k, h in enumerate(hp_imgs):
+                    h.copy_(imgs[k].cpu().repeat(-(-cnt // batch))[:cnt * IMG_BYTES])
+                hp_logits = [torch.empty(cnt, 1000, dtype=torch.float32).pin_memory() for _ in range(DEPTH)]
+                hp_top1 = [torch.empty(cnt, dtype=torch.int32).pin_memory() for _ in range(DEPTH)]
+                hp_prob = [torch.empty(cnt, dtype=torch.float32).pin_memory() for _ in range(DEPTH)]
+
+                def loop(count):
+                    pending = []
+                    for i in range(count):
+                        k = i % DEPTH
+                        pending.append(ctx.forward_submit(hp_imgs[k].data_ptr(), cnt, hp_logits[k].data_ptr(),
+                                                          hp_top1[k].data_ptr(), hp_prob[k].data_ptr()))
+                        if len(pending) == DEPTH:
+                            ctx.forward_wait(pending.pop(0))
+                    for t in pending:
+                        ctx.forward_wait(t)
+
+                loop(4)
+                fence()
+                reps = []
+                for _ in range(repetitions):
+                    dist.barrier()
+                    t0 = time.perf_counter()
+                    loop(ke)
+                    torch.cuda.synchronize(dev)
+                    reps.append(time.perf_counter() - t0)
+                tw = torch.tensor([sorted(reps)[len(reps) // 2]], dtype=torch.float64, device=dev)
+                tw_ranks = [tw.clone() for _ in range(world)]
+                dist.all_gather(tw_ranks, tw)
+                # the first images of the weighted shard are the equal-shard images of the same slot: same top-1
+                m = min(cnt, batch)
+                if not torch.equal(hp_top1[(ke - 1) % DEPTH][:m], h_top1[(ke - 1) % DEPTH][:m]):
+                    raise SystemExit("weighted-shard e2e and equal-shard e2e disagree on top-1")
+                return [float(t.item()) for t in tw_ranks], counts
+
+            _, link = h2d_ceiling(ctx, torch, dev, batch * IMG_BYTES, world, dist)
+            # calibration pass (untimed for the record): shares from the link rates, then from the rates the ranks reached
+            t_cal, c_cal = weighted_e2e(link, 1)
+            reached = [c / t for c, t in zip(c_cal, t_cal)]
+            tw_ranks, counts = weighted_e2e(reached, 3)
+            e2e_equal_value, e2e_equal_ranks = e2e_value, e2e_ranks
+            e2e_value, e2e_ranks = world * batch * ke / max(tw_ranks), tw_ranks
+            shard_info = {"images_per_rank": counts, "link_gbs": link, "calibration_pass_images_per_rank": c_cal,
+                          "how": "global batch cut by mnv1_dp_shard_weighted: first in proportion to each rank's pinned H2D "
+                                 "rate with all ranks copying, then (one untimed calibration pass of `steps` steps) in proportion "
+                                 "to the images/s each rank reached; the gather block keeps its world x batch rows "
+                                 "(mnv1_gather_set_rows)"}
+            if ctx.gather_active():
+                ctx.gather_set_rows(rank * batch, batch)
         # one blocking call (no overlap) for reference, and a consistency check of the pipelined outputs
         t0 = time.perf_counter()
         for _ in range(5):
@@ -453,13 +536,13 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         if not torch.equal(h_top1[0].to(dev), top1):
             raise SystemExit("e2e path and device path disagree on top-1")
-        ceiling_gbs = h2d_ceiling(ctx, torch, dev, batch * IMG_BYTES, world, dist)
+        ceiling_gbs, ceiling_ranks = h2d_ceiling(ctx, torch, dev, batch * IMG_BYTES, world, dist)
         ceiling_imgs = ceiling_gbs * 1e9 / IMG_BYTES
         # the same probe while the GPU runs forward passes (device-resident inputs) on the compute stream: what the link
         # delivers when the copy engine shares HBM / L2 with the kernels, i.e. under the conditions of the e2e loop
         for i in range(60):
             ctx.forward_device(imgs[i % N_ROTATE].data_ptr(), batch, logits.data_ptr(), top1.data_ptr(), prob.data_ptr())
-        loaded_gbs = h2d_ceiling(ctx, torch, dev, batch * IMG_BYTES, world, dist)
+        loaded_gbs, loaded_ranks = h2d_ceiling(ctx, torch, dev, batch * IMG_BYTES, world, dist)
         torch.cuda.synchronize(dev)
         loaded_imgs = loaded_gbs * 1e9 / IMG_BYTES
 
@@ -507,13 +590,23 @@ def run_ours(args):
                                 "each step streams ~5 GB of activations",
                           "cpu_affinity": numa},
                "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": batch * IMG_BYTES,
-                       "d2h_bytes_per_step": batch * 1000 * 4 + batch * 8, "steps": ke,
-                       "api": "mnv1_forward_submit/_wait (C-ABI, pinned host buffers, 3 batches in flight)",
+                       "d2h_bytes_per_step": batch * 1000 * 4 + batch * 8, "bytes_are": "per rank, mean over ranks",
+                       "steps": ke,
+                       "api": "mnv1_forward_submit/_wait (C-ABI, pinned host buffers, 3 batches in flight)"
+                              + ("" if world == 1 else "; shards of the global batch in proportion to the ranks' H2D rates"),
                        "timing": "wall clock, median of 3 repetitions of `steps` steps, max over ranks",
                        "blocking_call_value": round(e2e_blocking, 1),
-                       "h2d_ceiling": {"gbs_all_ranks": round(ceiling_gbs, 1), "images_per_s": round(ceiling_imgs, 1),
-                                       "how": "mnv1_h2d_probe: pinned cudaMemcpyAsync of one batch, 20 back to back over 3 rotating source buffers (the e2e working set), CUDA events, all ranks at once (sum)"},
-                       "h2d_ceiling_under_load": {"gbs_all_ranks": round(loaded_gbs, 1), "images_per_s": round(loaded_imgs, 1),
+                       "step_ms_per_rank": [round(t / ke * 1e3, 3) for t in e2e_ranks],
+                       "shards": shard_info,
+                       "equal_shards": None if e2e_equal_value is None else {
+                           "value": round(e2e_equal_value, 1),
+                           "step_ms_per_rank": [round(t / ke * 1e3, 3) for t in e2e_equal_ranks]},
+                       "h2d_ceiling": {"gbs_all_ranks": round(ceiling_gbs, 1), "gbs_per_rank": ceiling_ranks,
+                                       "images_per_s": round(ceiling_imgs, 1),
+                                       "images_per_s_if_every_rank_had_the_slowest_link": round(world * min(ceiling_ranks) * 1e9 / IMG_BYTES, 1),
+                                       "how": "mnv1_h2d_probe_*: pinned cudaMemcpyAsync of one batch back to back over 3 rotating source buffers (the e2e working set), CUDA events, all ranks start together and copy equally long (second pass: copy counts in proportion to the first pass' rates); sum over ranks"},
+                       "h2d_ceiling_under_load": {"gbs_all_ranks": round(loaded_gbs, 1), "gbs_per_rank": loaded_ranks,
+                                                  "images_per_s": round(loaded_imgs, 1),
                                                   "how": "the same probe while every GPU runs forward passes on its compute stream"},
                        "frac_of_min_kernel_or_h2d_ceiling": round(e2e_value / min(value, ceiling_imgs), 3),
                        "frac_of_min_kernel_or_h2d_ceiling_under_load": round(e2e_value / min(value, loaded_imgs), 3)},
@@ -544,7 +637,7 @@ def run_single_process(args):
     world = args.gpus
     batch = args.global_batch // world if args.global_batch else args.batch
     K, W = args.steps, max(args.warmup, 3)
-    dp = mn.DataParallel(list(range(world)), mn.BF16, max_batch_per_gpu=batch)
+    dp = mn.DataParallel(list(range(world)), mn.BF16, max_batch_per_gpu=batch * 3 // 2)   # room for uneven shards
     dp.set_pad_mode(mn.PAD_TFSAME); dp.set_input_transform(1 / 127.5, -1.0)
     dp.set_weights(synth.weights(), *synth.batchnorm(), mn.ACT_RELU6)
     imgs = []
@@ -571,18 +664,27 @@ def run_single_process(args):
         h[r * batch * IMG_BYTES:(r + 1) * batch * IMG_BYTES].copy_(imgs[0][r].cpu())
     hl = torch.empty(world * batch, 1000).pin_memory(); ht = torch.empty(world * batch, dtype=torch.int32).pin_memory()
     hp = torch.empty(world * batch).pin_memory()
-    pend = []
     ke = max(4, min(K, 50))
-    for i in range(3):
-        dp.forward_wait(dp.forward_submit(h.data_ptr(), world * batch, hl.data_ptr(), ht.data_ptr(), hp.data_ptr()))
-    t1 = time.perf_counter()
-    for i in range(ke):
-        pend.append(dp.forward_submit(h.data_ptr(), world * batch, hl.data_ptr(), ht.data_ptr(), hp.data_ptr()))
-        if len(pend) == 3:
-            dp.forward_wait(pend.pop(0))
-    for t in pend:
-        dp.forward_wait(t)
-    de = time.perf_counter() - t1
+
+    def e2e_run():
+        pend = []
+        for i in range(3):
+            dp.forward_wait(dp.forward_submit(h.data_ptr(), world * batch, hl.data_ptr(), ht.data_ptr(), hp.data_ptr()))
+        t1 = time.perf_counter()
+        for i in range(ke):
+            pend.append(dp.forward_submit(h.data_ptr(), world * batch, hl.data_ptr(), ht.data_ptr(), hp.data_ptr()))
+            if len(pend) == 3:
+                dp.forward_wait(pend.pop(0))
+        for t in pend:
+            dp.forward_wait(t)
+        return time.perf_counter() - t1
+
+    de_equal = sorted(e2e_run() for _ in range(3))[1]
+    top1_equal = ht.clone()
+    rates = dp.calibrate() if world > 1 else None      # shards in proportion to each GPU's concurrent H2D rate
+    de = sorted(e2e_run() for _ in range(3))[1] if world > 1 else de_equal
+    if not torch.equal(ht, top1_equal):
+        raise SystemExit("weighted shards changed the results")
     out = {"metric": METRIC, "value": round(world * batch * K / dt, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": round(dt / K * 1e3, 4), "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak",
            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -591,7 +693,10 @@ def run_single_process(args):
                                   "because every call drains all streams)",
                       "batch_per_gpu": batch, "global_batch": batch * world, "parallelism": f"dp{world} single process"},
            "e2e": {"value": round(world * batch * ke / de, 1), "unit": UNIT, "h2d_bytes_per_step": world * batch * IMG_BYTES,
-                   "d2h_bytes_per_step": world * batch * (1000 * 4 + 8), "api": "mnv1_dp_forward_submit/_wait"},
+                   "d2h_bytes_per_step": world * batch * (1000 * 4 + 8), "api": "mnv1_dp_forward_submit/_wait",
+                   "equal_shards_value": round(world * batch * ke / de_equal, 1),
+                   "shard_weights_gbs": None if rates is None else [round(x, 1) for x in rates],
+                   "shards": [mn.dp_shard_weighted(world * batch, r, world, rates)[1] for r in range(world)]},
            "clocks": clocks}
     print(json.dumps(out, default=float))
     dp.close()

@@ -270,6 +270,7 @@ class Context:
 
     def plan(self, max_batch: int):
         self._ck(lib().mnv1_plan(self.h, int(max_batch)))
+        self.planned_batch = max(int(max_batch), getattr(self, "planned_batch", 0))
 
     def forward(self, images_u8: np.ndarray, want_logits=True):
         """Host in / host out (H2D + 28 kernels + D2H inside)."""
@@ -318,6 +319,9 @@ class Context:
         self._ck(lib().mnv1_gather_create(self.h, world, rank, rows_per_rank))
         self._gather = True
 
+    def gather_set_rows(self, first_row: int, max_rows: int):
+        self._ck(lib().mnv1_gather_set_rows(self.h, C.c_long(first_row), int(max_rows)))
+
     def gather_active(self) -> bool:
         return getattr(self, "_gather", False)
 
@@ -340,6 +344,19 @@ class Context:
     def gather_destroy(self):
         self._ck(lib().mnv1_gather_destroy(self.h))
         self._gather = False
+
+    def h2d_probe_open(self, nbytes: int):
+        p = C.c_void_p()
+        self._ck(lib().mnv1_h2d_probe_open(self.h, C.c_size_t(nbytes), C.byref(p)))
+        return p
+
+    def h2d_probe_run(self, probe, reps: int) -> float:
+        g = C.c_float()
+        self._ck(lib().mnv1_h2d_probe_run(probe, int(reps), C.byref(g)))
+        return g.value
+
+    def h2d_probe_close(self, probe):
+        lib().mnv1_h2d_probe_close(probe)
 
     def h2d_probe(self, nbytes: int, reps: int = 20) -> float:
         g = C.c_float()
@@ -422,6 +439,19 @@ class DataParallel:
     def forward_wait(self, ticket: int):
         self._ck(lib().mnv1_dp_forward_wait(self.h, C.c_long(ticket)))
 
+    def set_shard_weights(self, weights=None):
+        if weights is None:
+            self._ck(lib().mnv1_dp_set_shard_weights(self.h, None))
+        else:
+            arr = (C.c_float * len(weights))(*[float(w) for w in weights])
+            self._ck(lib().mnv1_dp_set_shard_weights(self.h, arr))
+
+    def calibrate(self):
+        """Shards in proportion to each GPU's pinned H2D rate with all of them copying at once; returns the rates (GB/s)."""
+        arr = (C.c_float * self.size)()
+        self._ck(lib().mnv1_dp_calibrate(self.h, arr))
+        return list(arr)
+
     def forward_device(self, d_images: Sequence[int], n_per_gpu: int):
         arr = (C.c_void_p * len(d_images))(*d_images)
         self._ck(lib().mnv1_dp_forward_device(self.h, arr, int(n_per_gpu)))
@@ -438,6 +468,15 @@ class DataParallel:
 def dp_shard(n: int, rank: int, world: int):
     first, count = C.c_int(), C.c_int()
     rc = lib().mnv1_dp_shard(n, rank, world, C.byref(first), C.byref(count))
+    if rc:
+        raise Mnv1Error(rc, "bad shard arguments")
+    return first.value, count.value
+
+
+def dp_shard_weighted(n: int, rank: int, world: int, weights=None):
+    first, count = C.c_int(), C.c_int()
+    arr = None if weights is None else (C.c_float * len(weights))(*[float(w) for w in weights])
+    rc = lib().mnv1_dp_shard_weighted(n, rank, world, arr, C.byref(first), C.byref(count))
     if rc:
         raise Mnv1Error(rc, "bad shard arguments")
     return first.value, count.value

@@ -161,6 +161,7 @@ struct mnv1_ctx {
   // logits gather of the data-parallel mode (mnv1_gather_*): this rank's gather block, the peers' blocks it
   // stores into, and the HeadGather handed to the head kernel
   int g_world = 0, g_rank = 0, g_rows = 0;
+  long g_first = 0; int g_max = 0;   // this rank's window of the gather block (mnv1_gather_set_rows)
   uint8_t* g_block = nullptr;                 // [world*rows][1000] f32 | [world*rows] i32 | [world*rows] f32
   void* g_peer[8] = {};                       // base of rank d's block as mapped into this process / device
   bool g_peer_ipc[8] = {};
@@ -1081,7 +1082,7 @@ int mnv1_forward_device(mnv1_ctx* ctx, const void* d_images, int n, void* d_logi
   int rc = check_ready(ctx, n);
   if (rc) return rc;
   if (!d_images || !d_logits) return fail(ctx, MNV1_EINVAL, "forward_device: images and logits are required");
-  if (ctx->gather.n_dst && n > ctx->g_rows) return fail(ctx, MNV1_EINVAL, "forward: batch exceeds the gather block's rows_per_rank");
+  if (ctx->gather.n_dst && n > ctx->g_max) return fail(ctx, MNV1_EINVAL, "forward: batch exceeds this rank's rows of the gather block");
   if (!ctx->use_graph) {
     CK(ctx, enqueue_layers(ctx, (const uint8_t*)d_images, n, MNV1_NUM_LAYERS, (float*)d_logits, (int*)d_top1,
                            (float*)d_prob, nullptr, nullptr));
@@ -1325,7 +1326,7 @@ static void gather_rebuild(mnv1_ctx* ctx) {
     g.prob[g.n_dst] = (float*)(base + (size_t)total * (MNV1_NUM_CLASSES * 4 + 4));
     ++g.n_dst;
   }
-  g.row0 = (long)ctx->g_rank * ctx->g_rows;
+  g.row0 = ctx->g_first;
   ctx->gather = g;
   drop_graphs(ctx);                                        // captured graphs carry the old pointers
 }
@@ -1336,6 +1337,7 @@ static void gather_release(mnv1_ctx* ctx) {
   }
   cudaFree(ctx->g_block); ctx->g_block = nullptr;
   ctx->g_world = ctx->g_rank = ctx->g_rows = 0;
+  ctx->g_first = 0; ctx->g_max = 0;
   ctx->gather = mnv1::HeadGather{};
 }
 
@@ -1350,10 +1352,21 @@ int mnv1_gather_create(mnv1_ctx* ctx, int world, int rank, int rows_per_rank) {
   if (e != cudaSuccess) return fail(ctx, MNV1_ENOMEM, std::string("gather_create: ") + cudaGetErrorString(e));
   CK(ctx, cudaMemset(ctx->g_block, 0, gather_bytes(world * rows_per_rank)));
   ctx->g_world = world; ctx->g_rank = rank; ctx->g_rows = rows_per_rank;
+  ctx->g_first = (long)rank * rows_per_rank; ctx->g_max = rows_per_rank;
   ctx->g_peer[rank] = ctx->g_block;
   gather_rebuild(ctx);
   return MNV1_OK;
 }
+int mnv1_gather_set_rows(mnv1_ctx* ctx, long first_row, int max_rows) {
+  GUARD(ctx);
+  if (!ctx || !ctx->g_block) return fail(ctx, MNV1_ESTATE, "gather_set_rows: no gather block");
+  if (first_row < 0 || max_rows <= 0 || first_row + max_rows > (long)ctx->g_world * ctx->g_rows)
+    return fail(ctx, MNV1_EINVAL, "gather_set_rows: the window leaves the block of world * rows_per_rank rows");
+  ctx->g_first = first_row; ctx->g_max = max_rows;
+  gather_rebuild(ctx);
+  return MNV1_OK;
+}
+
 int mnv1_gather_export(mnv1_ctx* ctx, void* handle64) {
   GUARD(ctx);
   if (!ctx || !handle64 || !ctx->g_block) return fail(ctx, MNV1_ESTATE, "gather_export: call mnv1_gather_create first");
@@ -1494,33 +1507,68 @@ int mnv1_profile_prefixes(mnv1_ctx* ctx, const void* d_images, int n, int iters,
 // the context's copy stream, CUDA events.  The copies rotate over THREE pinned source buffers, like the three
 // batches mnv1_forward_submit keeps in flight: a single buffer copied again and again is served from the CPU's
 // last-level cache and overstates what the host's DRAM can feed the link.  The ceiling of mnv1_forward's upload.
-int mnv1_h2d_probe(mnv1_ctx* ctx, size_t bytes, int reps, float* gbytes_per_s) {
-  GUARD(ctx);
-  if (!ctx || !bytes || reps <= 0 || !gbytes_per_s) return fail(ctx, MNV1_EINVAL, "h2d_probe: bad arguments");
+struct mnv1_h2d_probe_t {
+  mnv1_ctx* ctx = nullptr;
+  size_t bytes = 0;
   void* h[3] = {nullptr, nullptr, nullptr};
   void* d = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  cudaError_t e = cudaMalloc(&d, bytes);
-  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
-    e = cudaMallocHost(&h[i], bytes);
-    if (e == cudaSuccess) memset(h[i], i + 1, bytes);
-  }
-  if (e == cudaSuccess) e = cudaEventCreate(&e0);
-  if (e == cudaSuccess) e = cudaEventCreate(&e1);
-  for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaMemcpyAsync(d, h[i], bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
-  if (e == cudaSuccess) e = cudaEventRecord(e0, ctx->copy_stream);
-  for (int i = 0; i < reps && e == cudaSuccess; ++i) e = cudaMemcpyAsync(d, h[i % 3], bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
-  if (e == cudaSuccess) e = cudaEventRecord(e1, ctx->copy_stream);
-  if (e == cudaSuccess) e = cudaEventSynchronize(e1);
-  float ms = 0.f;
-  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
-  if (e0) cudaEventDestroy(e0);
-  if (e1) cudaEventDestroy(e1);
-  cudaFree(d);
-  for (int i = 0; i < 3; ++i) cudaFreeHost(h[i]);
-  if (e != cudaSuccess) return fail_cuda(ctx, e, "h2d_probe");
-  *gbytes_per_s = (float)((double)bytes * reps / (ms * 1e-3) / 1e9);
+};
+
+int mnv1_h2d_probe_close(mnv1_h2d_probe_t* p) {
+  if (!p) return MNV1_OK;
+  GUARD(p->ctx);
+  if (p->e0) cudaEventDestroy(p->e0);
+  if (p->e1) cudaEventDestroy(p->e1);
+  cudaFree(p->d);
+  for (int i = 0; i < 3; ++i) cudaFreeHost(p->h[i]);
+  delete p;
   return MNV1_OK;
+}
+
+int mnv1_h2d_probe_open(mnv1_ctx* ctx, size_t bytes, mnv1_h2d_probe_t** out) {
+  GUARD(ctx);
+  if (!ctx || !bytes || !out) return fail(ctx, MNV1_EINVAL, "h2d_probe: bad arguments");
+  mnv1_h2d_probe_t* p = new mnv1_h2d_probe_t;
+  p->ctx = ctx; p->bytes = bytes;
+  cudaError_t e = cudaMalloc(&p->d, bytes);
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+    e = cudaHostAlloc(&p->h[i], bytes, getenv("MNV1_H2D_WC") ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (e == cudaSuccess) memset(p->h[i], i + 1, bytes);
+  }
+  if (e == cudaSuccess) e = cudaEventCreate(&p->e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&p->e1);
+  if (e != cudaSuccess) { mnv1_h2d_probe_close(p); return fail_cuda(ctx, e, "h2d_probe_open"); }
+  *out = p;
+  return MNV1_OK;
+}
+
+int mnv1_h2d_probe_run(mnv1_h2d_probe_t* p, int reps, float* gbytes_per_s) {
+  if (!p || reps <= 0 || !gbytes_per_s) return MNV1_EINVAL;
+  mnv1_ctx* ctx = p->ctx;
+  GUARD(ctx);
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMemcpyAsync(p->d, p->h[i], p->bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+  if (e == cudaSuccess) e = cudaEventRecord(p->e0, ctx->copy_stream);
+  for (int i = 0; i < reps && e == cudaSuccess; ++i)
+    e = cudaMemcpyAsync(p->d, p->h[(i + 2) % 3], p->bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+  if (e == cudaSuccess) e = cudaEventRecord(p->e1, ctx->copy_stream);
+  if (e == cudaSuccess) e = cudaEventSynchronize(p->e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, p->e0, p->e1);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "h2d_probe_run");
+  *gbytes_per_s = (float)((double)p->bytes * reps / (ms * 1e-3) / 1e9);
+  return MNV1_OK;
+}
+
+int mnv1_h2d_probe(mnv1_ctx* ctx, size_t bytes, int reps, float* gbytes_per_s) {
+  if (!ctx || !bytes || reps <= 0 || !gbytes_per_s) return fail(ctx, MNV1_EINVAL, "h2d_probe: bad arguments");
+  mnv1_h2d_probe_t* p = nullptr;
+  int rc = mnv1_h2d_probe_open(ctx, bytes, &p);
+  if (rc) return rc;
+  rc = mnv1_h2d_probe_run(p, reps, gbytes_per_s);
+  mnv1_h2d_probe_close(p);
+  return rc;
 }
 
 int mnv1_synth_images_device(mnv1_ctx* ctx, void* d_images, int n, long first, uint64_t seed) {

@@ -69,6 +69,7 @@ struct mnv1_dp {
   std::vector<mnv1_ctx*> ctx;
   std::vector<std::unique_ptr<Worker>> workers;
   std::string err;
+  std::vector<float> weight;   // shard weights (mnv1_dp_set_shard_weights / mnv1_dp_calibrate); empty = equal shards
   // tickets of mnv1_dp_forward_submit: per-rank tickets of the last kRing submits
   static constexpr int kRing = 8;
   long next_ticket = 0;
@@ -103,6 +104,39 @@ int mnv1_dp_shard(int n, int rank, int world, int* first, int* count) {
   const int base = n / world, rem = n % world;
   *first = rank * base + (rank < rem ? rank : rem);
   *count = base + (rank < rem ? 1 : 0);
+  return MNV1_OK;
+}
+
+int mnv1_dp_shard_weighted(int n, int rank, int world, const float* weight, int* first, int* count) {
+  if (!weight) return mnv1_dp_shard(n, rank, world, first, count);
+  if (world <= 0 || world > 64 || rank < 0 || rank >= world || n < 0 || !first || !count) return MNV1_EINVAL;
+  double sum = 0;
+  for (int r = 0; r < world; ++r) {
+    if (!(weight[r] > 0.f)) return MNV1_EINVAL;   // also rejects NaN
+    sum += weight[r];
+  }
+  // largest-remainder apportionment: floor of the exact share, the leftover images to the largest fractions
+  // (ties to the lower rank), so the counts add up to n and differ from the exact share by less than one image
+  int cnt[64];
+  double frac[64];
+  int given = 0;
+  for (int r = 0; r < world; ++r) {
+    const double share = (double)n * weight[r] / sum;
+    cnt[r] = (int)share;
+    frac[r] = share - cnt[r];
+    given += cnt[r];
+  }
+  for (; given < n; ++given) {
+    int best = 0;
+    for (int r = 1; r < world; ++r)
+      if (frac[r] > frac[best]) best = r;
+    ++cnt[best];
+    frac[best] = -1.0;
+  }
+  int f = 0;
+  for (int r = 0; r < rank; ++r) f += cnt[r];
+  *first = f;
+  *count = cnt[rank];
   return MNV1_OK;
 }
 
@@ -178,15 +212,55 @@ int mnv1_dp_load_weights(mnv1_dp* dp, const char* path, mnv1_act act) {
 
 static const size_t kImg = 224 * 224 * 3;
 
+int mnv1_dp_set_shard_weights(mnv1_dp* dp, const float* weight) {
+  if (!dp) return MNV1_EINVAL;
+  if (!weight) { dp->weight.clear(); return MNV1_OK; }
+  for (int r = 0; r < dp->n; ++r)
+    if (!(weight[r] > 0.f)) { dp->err = "dp_set_shard_weights: weights must be positive"; return MNV1_EINVAL; }
+  dp->weight.assign(weight, weight + dp->n);
+  return MNV1_OK;
+}
+
+// The host feeds its GPUs unevenly when they all copy at once (one memory controller nearer than the other, shared
+// PCIe switches; a guest may not even see the topology): measure every GPU's pinned H2D rate with all of them copying
+// and cut the batch in proportion, so that the uploads of a step finish together.
+int mnv1_dp_calibrate(mnv1_dp* dp, float* gbytes_per_s) {
+  if (!dp) return MNV1_EINVAL;
+  std::vector<float> rate(dp->n, 0.f);
+  std::vector<mnv1_h2d_probe_t*> probe(dp->n, nullptr);
+  const size_t bytes = (size_t)dp->rows_per_gpu * kImg;
+  // allocate everywhere first: pinning takes tens of milliseconds and the copies must overlap
+  int rc = dp->all([&](int r) { return mnv1_h2d_probe_open(dp->ctx[r], bytes, &probe[r]); });
+  if (!rc) rc = dp->all([&](int r) { return mnv1_h2d_probe_run(probe[r], 12, &rate[r]); });
+  if (!rc) {
+    // the GPUs with the fast links finished early and left the others alone with the memory system: repeat with
+    // copy counts in proportion to the first rates, so that everybody copies until the end
+    float top = 0.f;
+    for (float x : rate) top = x > top ? x : top;
+    std::vector<int> reps(dp->n);
+    for (int r = 0; r < dp->n; ++r) reps[r] = (int)(30.f * rate[r] / top + 0.5f) < 4 ? 4 : (int)(30.f * rate[r] / top + 0.5f);
+    rc = dp->all([&](int r) { return mnv1_h2d_probe_run(probe[r], reps[r], &rate[r]); });
+  }
+  dp->all([&](int r) { return mnv1_h2d_probe_close(probe[r]); });
+  if (rc) return rc;
+  if (gbytes_per_s) std::memcpy(gbytes_per_s, rate.data(), sizeof(float) * dp->n);
+  return mnv1_dp_set_shard_weights(dp, rate.data());
+}
+
 int mnv1_dp_forward_submit(mnv1_dp* dp, const uint8_t* images, int n, float* logits, int* top1, float* top1_prob,
                            long* ticket) {
   if (!dp || !images || !ticket || n <= 0) return MNV1_EINVAL;
-  if ((n + dp->n - 1) / dp->n > dp->rows_per_gpu) { dp->err = "dp_forward: batch exceeds n_devices * max_batch_per_gpu"; return MNV1_EINVAL; }
+  const float* wt = dp->weight.empty() ? nullptr : dp->weight.data();
+  for (int r = 0; r < dp->n; ++r) {
+    int first = 0, count = 0;
+    mnv1_dp_shard_weighted(n, r, dp->n, wt, &first, &count);
+    if (count > dp->rows_per_gpu) { dp->err = "dp_forward: a shard exceeds max_batch_per_gpu"; return MNV1_EINVAL; }
+  }
   const int slot = (int)(dp->next_ticket % mnv1_dp::kRing);
   std::vector<long>& rt = dp->rank_ticket[slot];
   int rc = dp->all([&](int r) {
     int first = 0, count = 0;
-    mnv1_dp_shard(n, r, dp->n, &first, &count);
+    mnv1_dp_shard_weighted(n, r, dp->n, wt, &first, &count);
     rt[r] = -1;
     if (count == 0) return MNV1_OK;
     return mnv1_forward_submit(dp->ctx[r], images + (size_t)first * kImg, count,

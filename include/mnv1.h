@@ -185,6 +185,12 @@ int mnv1_profile_prefixes(mnv1_ctx* ctx, const void* d_images_u8, int n, int ite
 /* GB/s of `reps` back-to-back pinned cudaMemcpyAsync host-to-device copies of `bytes` (the ceiling of the
  * upload inside mnv1_forward; replaces nothing in the reference, whose clEnqueueWriteBuffer is blocking) */
 int mnv1_h2d_probe(mnv1_ctx* ctx, size_t bytes, int reps, float* gbytes_per_s);
+/* the same in three steps, so that several ranks can allocate first (open: device buffer + three pinned source
+ * buffers), then start copying TOGETHER (run, after the caller's barrier; may be repeated), then free (close) */
+typedef struct mnv1_h2d_probe_t mnv1_h2d_probe_t;
+int mnv1_h2d_probe_open(mnv1_ctx* ctx, size_t bytes, mnv1_h2d_probe_t** probe);
+int mnv1_h2d_probe_run(mnv1_h2d_probe_t* probe, int reps, float* gbytes_per_s);
+int mnv1_h2d_probe_close(mnv1_h2d_probe_t* probe);
 /* fill d_images (u8 [n][224][224][3]) with the synthetic stream of SURVEY §8(d): images
  * first..first+n-1 of seed `seed`, generated on the device */
 int mnv1_synth_images_device(mnv1_ctx* ctx, void* d_images_u8, int n, long first, uint64_t seed);
@@ -223,6 +229,9 @@ const char* mnv1_version(void);
  * from now on mnv1_forward* on this context (n <= rows_per_rank) also writes rows rank*rows_per_rank + i of
  * every attached / imported block.  bf16 contexts. */
 int mnv1_gather_create(mnv1_ctx* ctx, int world, int rank, int rows_per_rank);
+/* uneven shards: this rank's rows land at [first_row, first_row + max_rows) of the block instead (forward needs
+ * n <= max_rows); the block keeps world * rows_per_rank rows, e.g. the shards of mnv1_dp_shard_weighted */
+int mnv1_gather_set_rows(mnv1_ctx* ctx, long first_row, int max_rows);
 /* peers in the SAME process (cudaDeviceEnablePeerAccess): make ctx store into peer's block */
 int mnv1_gather_attach(mnv1_ctx* ctx, mnv1_ctx* peer);
 /* peers in OTHER processes (one process per GPU): exchange the 64-byte CUDA IPC handle by any means */
@@ -247,6 +256,15 @@ int mnv1_dp_load_weights(mnv1_dp* dp, const char* path, mnv1_act act);
 /* shard of rank r of g for a batch of n: images [first, first + count) — contiguous, the remainder spread
  * over the first ranks */
 int mnv1_dp_shard(int n, int rank, int world, int* first, int* count);
+/* the same with shards in proportion to weight[0..world) (> 0; NULL = equal): floor of the exact share, the
+ * leftover images to the largest fractions.  For boxes that feed their GPUs unevenly (see mnv1_dp_calibrate). */
+int mnv1_dp_shard_weighted(int n, int rank, int world, const float* weight, int* first, int* count);
+/* shard weights of mnv1_dp_forward* (NULL = equal shards again); every shard must still fit max_batch_per_gpu */
+int mnv1_dp_set_shard_weights(mnv1_dp* dp, const float* weight);
+/* measure each GPU's pinned host->device rate with ALL of them copying at once (mnv1_h2d_probe_*; a second pass
+ * gives every GPU a copy count in proportion to its first rate, so that all finish together and the rates are those of
+ * the steady state) and use the rates as shard weights; gbytes_per_s (may be NULL) receives the n_devices rates */
+int mnv1_dp_calibrate(mnv1_dp* dp, float* gbytes_per_s);
 /* host in / host out like mnv1_forward, the batch cut into contiguous shards; every GPU copies its shard of
  * the outputs straight into the caller's arrays.  submit/wait as for mnv1_forward_submit/_wait. */
 int mnv1_dp_forward(mnv1_dp* dp, const uint8_t* images, int n, float* logits, int* top1, float* top1_prob);

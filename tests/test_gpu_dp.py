@@ -145,3 +145,75 @@ def test_fused_head_matches_three_kernel_head(mn, synth_net, monkeypatch):
     want_l = np.load(path)
     assert np.array_equal(got_l, want_l)
     assert got_t.tolist() == json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_dp_weighted_shards_and_calibration_keep_the_results(mn, synth_net):
+    """uneven shards (mnv1_dp_set_shard_weights, or mnv1_dp_calibrate = weights from each GPU's measured pinned H2D rate
+    with all GPUs copying): the batch is cut differently, the outputs are bit-identical to the single-context run."""
+    from mnv1_b200 import synth
+    w, sc, sh = synth_net
+    world, n = 4, 41
+    img = synth.images(n)
+    want_l, want_t, want_p = _single(mn, synth_net, img)
+    dp = mn.DataParallel(_devices(world), mn.BF16, max_batch_per_gpu=24)
+    dp.set_pad_mode(mn.PAD_TFSAME); dp.set_input_transform(1 / 127.5, -1.0); dp.set_weights(w, sc, sh, mn.ACT_RELU6)
+    weights = [1.0, 2.5, 0.5, 2.0]
+    counts = [mn.dp_shard_weighted(n, r, world, weights)[1] for r in range(world)]
+    assert sum(counts) == n and counts[1] > counts[0] > counts[2]
+    dp.set_shard_weights(weights)
+    lg, t1, p1 = dp.forward(img)
+    assert np.array_equal(lg, want_l) and np.array_equal(t1, want_t) and np.array_equal(p1, want_p)
+    with pytest.raises(mn.Mnv1Error):
+        dp.forward(synth.images(64))         # rank 1's share of 64 images exceeds max_batch_per_gpu = 24
+    with pytest.raises(mn.Mnv1Error):
+        dp.set_shard_weights([1.0, 0.0, 1.0, 1.0])
+    rates = dp.calibrate()
+    assert len(rates) == world and all(r > 0.5 for r in rates)      # GB/s
+    lg, t1, _ = dp.forward(img)
+    assert np.array_equal(lg, want_l) and np.array_equal(t1, want_t)
+    dp.set_shard_weights(None)
+    lg, _, _ = dp.forward(img)
+    assert np.array_equal(lg, want_l)
+    dp.close()
+
+
+def test_gather_rows_window_for_uneven_shards(mn, synth_net):
+    """mnv1_gather_set_rows: two ranks with 11 + 5 images of a 16-row block (2 x 8) — rank 0's rows land at 0..10,
+    rank 1's at 11..15, and the block equals the single-context run."""
+    import torch
+    from mnv1_b200 import synth
+    w, sc, sh = synth_net
+    devs = _devices(2)
+    ctxs = []
+    for r in range(2):
+        c = mn.Context(devs[r], mn.BF16)
+        c.set_pad_mode(mn.PAD_TFSAME); c.set_input_transform(1 / 127.5, -1.0); c.set_weights(w, sc, sh, mn.ACT_RELU6)
+        c.gather_create(2, r, 8)
+        ctxs.append(c)
+    ctxs[0].gather_attach(ctxs[1]); ctxs[1].gather_attach(ctxs[0])
+    spans = [mn.dp_shard_weighted(16, r, 2, [11.0, 5.0]) for r in range(2)]
+    assert spans == [(0, 11), (11, 5)]
+    with pytest.raises(mn.Mnv1Error):
+        ctxs[1].gather_set_rows(11, 6)       # leaves the 16-row block
+    for r in range(2):
+        ctxs[r].gather_set_rows(*spans[r])
+    img = synth.images(16)
+    want_l, want_t, _ = _single(mn, synth_net, img)
+    keep = []
+    for r in range(2):
+        first, cnt = spans[r]
+        with torch.cuda.device(devs[r]):
+            d = torch.from_numpy(img[first:first + cnt].copy()).to(f"cuda:{devs[r]}")
+            lg = torch.empty(cnt, 1000, device=f"cuda:{devs[r]}"); t1 = torch.empty(cnt, dtype=torch.int32, device=f"cuda:{devs[r]}")
+            ctxs[r].forward_device(d.data_ptr(), cnt, lg.data_ptr(), t1.data_ptr())
+            keep.append((d, lg, t1))
+    for c in ctxs:
+        c.sync()
+    for r in range(2):
+        lp, tp, _ = ctxs[r].gather_ptrs()
+        assert np.array_equal(_from_ptr(torch, lp, (16, 1000), torch.float32, devs[r]).cpu().numpy(), want_l)
+        assert np.array_equal(_from_ptr(torch, tp, (16,), torch.int32, devs[r]).cpu().numpy(), want_t)
+    with pytest.raises(mn.Mnv1Error):
+        ctxs[1].forward(synth.images(6))     # more rows than rank 1's window
+    for c in ctxs:
+        c.close()

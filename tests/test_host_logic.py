@@ -191,3 +191,29 @@ def test_dp_shard_matches_python_sharding():
             assert cover == list(range(n))
     with pytest.raises(mn.Mnv1Error):
         mn.dp_shard(4, 2, 2)
+
+
+def test_dp_shard_weighted_apportions_the_batch():
+    """mnv1_dp_shard_weighted (C-ABI, no GPU needed): contiguous cover of the batch, counts within one image of the exact
+    share, equal weights == mnv1_dp_shard, bad weights rejected."""
+    rng = np.random.default_rng(5)
+    rates = [27.2, 25.8, 25.0, 24.4, 38.2, 37.8, 37.7, 38.7]          # GB/s per GPU measured on an 8 x B200 box
+    for n in (0, 1, 7, 256, 2048, 2049):
+        for world in (1, 2, 3, 8):
+            for w in ([1.0] * world, rates[:world], list(rng.uniform(0.1, 5.0, world))):
+                cover, counts = [], []
+                for r in range(world):
+                    first, count = mn.dp_shard_weighted(n, r, world, w)
+                    cover += list(range(first, first + count))
+                    counts.append(count)
+                assert cover == list(range(n))
+                for r in range(world):
+                    assert abs(counts[r] - n * w[r] / sum(w)) < 1.0 + 1e-6
+            for r in range(world):
+                assert mn.dp_shard_weighted(n, r, world, [3.0] * world) == mn.dp_shard(n, r, world)
+                assert mn.dp_shard_weighted(n, r, world, None) == mn.dp_shard(n, r, world)
+    first, count = mn.dp_shard_weighted(2048, 0, 8, rates)
+    assert count < 256 < mn.dp_shard_weighted(2048, 7, 8, rates)[1]
+    for bad in ([1.0, 0.0], [1.0, -2.0], [float("nan"), 1.0]):
+        with pytest.raises(mn.Mnv1Error):
+            mn.dp_shard_weighted(16, 0, 2, bad)
