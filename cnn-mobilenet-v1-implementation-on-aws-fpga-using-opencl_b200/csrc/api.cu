@@ -510,6 +510,7 @@ static int create_filter_u8(mnv1_ctx* ctx, mnv1_filter* f, const float* w, const
   if (!packed.empty()) {
     if (cudaMalloc(&f->w_q32, packed.size() * 4) != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "cudaMalloc(filter) failed");
     CK(ctx, cudaMemcpy(f->w_q32, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    if (f->kind == MNV1_CONVOLUTE) f->h_q32 = packed;
   } else {
     if (cudaMalloc(&f->w_s8, cnt) != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "cudaMalloc(filter) failed");
     CK(ctx, cudaMemcpy(f->w_s8, q.data(), cnt, cudaMemcpyHostToDevice));
@@ -522,6 +523,7 @@ static int create_filter_u8(mnv1_ctx* ctx, mnv1_filter* f, const float* w, const
     }
     if (cudaMalloc(&f->bias_i32, (size_t)cout * 4) != cudaSuccess) return fail(ctx, MNV1_ENOMEM, "cudaMalloc(filter) failed");
     CK(ctx, cudaMemcpy(f->bias_i32, b.data(), (size_t)cout * 4, cudaMemcpyHostToDevice));
+    if (f->kind == MNV1_CONVOLUTE) f->h_bias = b;
   }
   return MNV1_OK;
 }

@@ -45,6 +45,7 @@ struct mnv1_filter {
   int* w_q32 = nullptr;
   int* bias_i32 = nullptr;
   int rshift = 0;
+  std::vector<int> h_q32, h_bias;   // stem: host copies (the integer stem reads them from the constant bank)
   CUtensorMap tmap_b;       // TMA descriptor of w_bf16 (pointwise, bf16 contexts)
   bool has_tmap = false;
   int tmap_bn = 0;          // N-tile the descriptor's box was built for

@@ -54,7 +54,7 @@ __device__ __forceinline__ int finish(int acc, int bias, int relu, int rshift) {
 }
 
 // ------------------------------------------------------------------------------------------ pointwise / FC
-constexpr int I8_BM = 128, I8_STAGES = 4, I8_THREADS = 192;
+constexpr int I8_BM = 128, I8_STAGES = 4, I8_THREADS = 320;   // TMA producer, MMA issuer, 8 epilogue warps
 
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -77,6 +77,7 @@ struct I8Params {
   const int* bias;       // [Cout] or nullptr
   long M;
   int K, Cout, relu, rshift, wrap;
+  int res;               // the CTA's filter tile (all k-blocks) stays in shared memory; CTAs are bound to an n-tile
 };
 
 // out[M][Cout] = store_u8(finish(in[M][K] . w[Cout][K]^T)).  Persistent CTAs loop over (128-row tile, BN-column tile)
@@ -106,15 +107,32 @@ __global__ void __launch_bounds__(I8_THREADS) pointwise_i8_kernel(const __grid_c
   constexpr int I8_BK = KB;
   constexpr uint32_t A_BYTES = I8_BM * I8_BK, B_BYTES = BN * I8_BK, STAGE = A_BYTES + B_BYTES;
   constexpr uint32_t ACC = BN < 32 ? 32 : BN, TM_COLS = 2 * ACC;
+  constexpr int EPI_HALVES = BN >= 64 ? 2 : 1;           // two epilogue warps per TMEM lane quarter, each takes half the columns
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = smem + I8_STAGES * STAGE;
-  const uint32_t full = bars, empty = bars + 8u * I8_STAGES, tm_full = empty + 8u * I8_STAGES, tm_empty = tm_full + 16, tmem_slot = tm_empty + 16;
-  const uint32_t sBias = tmem_slot + 16;                    // [n_tiles * BN] s32, zero past Cout: the epilogue reads it with broadcast LDS.128
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = (p.K + I8_BK - 1) / I8_BK;
   const int n_tiles = (p.Cout + BN - 1) / BN;
-  const long units = ((p.M + I8_BM - 1) / I8_BM) * n_tiles;
+  const long m_tiles = (p.M + I8_BM - 1) / I8_BM;
+  const long units = m_tiles * n_tiles;
+  // Shared memory: p.res = 0: a ring of (A, B) k-block pairs.  p.res = 1: the CTA works on ONE n-tile for its whole life
+  // (CTA c: n-tile c % n_tiles, m-tiles c / n_tiles, + gridDim.x / n_tiles, ...), its filter tile — all k-blocks —
+  // is loaded once and the ring carries A only: a third of the L2 -> SM traffic of a 512 -> 512 layer, and half the
+  // TMA issues (a thread starts a bulk copy every ~380 cycles).
+  const bool res = p.res != 0;
+  const uint32_t ring_bytes = res ? (uint32_t)I8_STAGES * A_BYTES + (uint32_t)num_kb * B_BYTES : (uint32_t)I8_STAGES * STAGE;
+  const uint32_t bars = smem + ring_bytes;
+  const uint32_t full = bars, empty = bars + 8u * I8_STAGES, tm_full = empty + 8u * I8_STAGES, tm_empty = tm_full + 16,
+                 b_full = tm_empty + 16, tmem_slot = b_full + 16;   // sBias stays 16-byte aligned
+  const uint32_t sBias = tmem_slot + 16;                    // [n_tiles * BN] s32, zero past Cout: the epilogue reads it with broadcast LDS.128
+  auto a_addr = [&](int s) { return smem + (uint32_t)s * (res ? A_BYTES : STAGE); };
+  auto b_addr = [&](int s, int kb) { return res ? smem + (uint32_t)I8_STAGES * A_BYTES + (uint32_t)kb * B_BYTES : smem + (uint32_t)s * STAGE + A_BYTES; };
+  // this CTA's it-th unit
+  const long my_first = res ? blockIdx.x / n_tiles : blockIdx.x, my_step = res ? gridDim.x / n_tiles : gridDim.x;
+  const long my_end = res ? m_tiles : units;
+  const int my_n = res ? (int)(blockIdx.x % n_tiles) * BN : 0;
+  auto unit_m = [&](long u) { return (int)(res ? u : u / n_tiles) * I8_BM; };
+  auto unit_n = [&](long u) { return res ? my_n : (int)(u % n_tiles) * BN; };
   if (p.bias) {
     int* sb = reinterpret_cast<int*>(smem_raw + (sBias - smem_u32(smem_raw)));
     for (int i = threadIdx.x; i < n_tiles * BN; i += I8_THREADS) sb[i] = i < p.Cout ? __ldg(p.bias + i) : 0;
@@ -123,7 +141,8 @@ __global__ void __launch_bounds__(I8_THREADS) pointwise_i8_kernel(const __grid_c
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b);
     for (int s = 0; s < I8_STAGES; ++s) { mbar_init(full + 8u * s, 1); mbar_init(empty + 8u * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tm_full + 8u * a, 1); mbar_init(tm_empty + 8u * a, 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tm_full + 8u * a, 1); mbar_init(tm_empty + 8u * a, 4 * EPI_HALVES); }
+    mbar_init(b_full, 1);
     mbar_init_fence();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TM_COLS);
@@ -132,23 +151,20 @@ __global__ void __launch_bounds__(I8_THREADS) pointwise_i8_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = lds32(tmem_slot);
 
-  // A filter that is a single (n-tile, k-block) — the first layers — is loaded ONCE per CTA, into stage 0's B slot, and
-  // every MMA reads it from there; the ring then carries A only (one TMA
-  // issue per tile instead of two: a thread starts a bulk copy every ~380 cycles).
-  const bool resident_b = n_tiles == 1 && num_kb == 1;
   if (warp == 0) {
     if (lane == 0) {
+      if (res && my_first < my_end) {
+        mbar_expect_tx(b_full, (uint32_t)num_kb * B_BYTES);
+        for (int kb = 0; kb < num_kb; ++kb) tma_load_2d(b_addr(0, kb), &tmap_b, b_full, kb * I8_BK, my_n);
+      }
       int s = 0; uint32_t ph = 0;
-      bool first = true;
-      for (long u = blockIdx.x; u < units; u += gridDim.x) {
-        const int m_idx = (int)(u / n_tiles) * I8_BM, n_idx = (int)(u % n_tiles) * BN;
+      for (long u = my_first; u < my_end; u += my_step) {
+        const int m_idx = unit_m(u), n_idx = unit_n(u);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty + 8u * s, ph ^ 1u);
-          const bool load_b = !resident_b || first;
-          mbar_expect_tx(full + 8u * s, load_b ? STAGE : A_BYTES);
-          tma_load_2d(smem + s * STAGE, &tmap_a, full + 8u * s, kb * I8_BK, m_idx);
-          if (load_b) tma_load_2d(smem + (resident_b ? 0u : (uint32_t)s * STAGE) + A_BYTES, &tmap_b, full + 8u * s, kb * I8_BK, n_idx);
-          first = false;
+          mbar_expect_tx(full + 8u * s, res ? A_BYTES : STAGE);
+          tma_load_2d(a_addr(s), &tmap_a, full + 8u * s, kb * I8_BK, m_idx);
+          if (!res) tma_load_2d(b_addr(s, kb), &tmap_b, full + 8u * s, kb * I8_BK, n_idx);
           if (++s == I8_STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -158,15 +174,16 @@ __global__ void __launch_bounds__(I8_THREADS) pointwise_i8_kernel(const __grid_c
       constexpr uint32_t idesc = umma_idesc_u8s8_m128(BN);
       int s = 0; uint32_t ph = 0;
       int as = 0; uint32_t aph = 0;
-      for (long u = blockIdx.x; u < units; u += gridDim.x) {
+      if (res && my_first < my_end) mbar_wait(b_full, 0u);
+      for (long u = my_first; u < my_end; u += my_step) {
         mbar_wait(tm_empty + 8u * as, aph ^ 1u);          // the epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)as * ACC;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full + 8u * s, ph);
           tc_fence_after();
-          const uint64_t da = umma_desc_kmajor<KB>(smem + s * STAGE);
-          const uint64_t db = umma_desc_kmajor<KB>(smem + (resident_b ? 0u : (uint32_t)s * STAGE) + A_BYTES);
+          const uint64_t da = umma_desc_kmajor<KB>(a_addr(s));
+          const uint64_t db = umma_desc_kmajor<KB>(b_addr(s, kb));
 #pragma unroll
           for (int k = 0; k < I8_BK / 32; ++k) umma_i8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) ? 1u : 0u);
           umma_commit(empty + 8u * s);
@@ -176,17 +193,21 @@ __global__ void __launch_bounds__(I8_THREADS) pointwise_i8_kernel(const __grid_c
         if (++as == 2) { as = 0; aph ^= 1u; }
       }
     }
-  } else {
-    const int quarter = warp & 3;
+  } else if ((warp - 2) / 4 < EPI_HALVES) {
+    // two warps per TMEM lane quarter (warp % 4): warps 2..5 take the first half of the tile's columns, 6..9 the second —
+    // one warp per scheduler could not keep up with the tensor pipe (every instruction waited out its own latency)
+    const int quarter = warp & 3, half = (warp - 2) / 4;
+    constexpr int C_LO_STEP = BN / EPI_HALVES < 32 ? 32 : BN / EPI_HALVES;
+    const int c_lo = half * C_LO_STEP, c_hi = c_lo + C_LO_STEP < BN ? c_lo + C_LO_STEP : (BN < 32 ? 32 : BN);
     const bool vec = (p.Cout & 31) == 0;                    // 32-byte rows pieces: one 256-bit store = one full sector
     int as = 0; uint32_t aph = 0;
-    for (long u = blockIdx.x; u < units; u += gridDim.x) {
-      const int m_idx = (int)(u / n_tiles) * I8_BM, n_idx = (int)(u % n_tiles) * BN;
+    for (long u = my_first; u < my_end; u += my_step) {
+      const int m_idx = unit_m(u), n_idx = unit_n(u);
       const long row = (long)m_idx + quarter * 32 + lane;
       mbar_wait(tm_full + 8u * as, aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         uint32_t v[32];
         tmem_ld32_nowait(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)as * ACC + (uint32_t)c0, v);
         tmem_ld_wait();
@@ -262,15 +283,25 @@ cudaError_t encode_u8(CUtensorMap* map, const void* base, uint64_t rows, uint64_
 }
 
 template <int BN, int KB>
-cudaError_t launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, const I8Params& p, int num_sms, cudaStream_t st) {
+cudaError_t launch_i8(const CUtensorMap& ta, const CUtensorMap& tb, I8Params p, int num_sms, cudaStream_t st) {
   constexpr int I8_BK = KB;
-  const size_t smem = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + BN * I8_BK) + 16 * I8_STAGES + 64 + (size_t)((p.Cout + BN - 1) / BN) * BN * 4;
-  cudaError_t e = ensure_dyn_smem((const void*)pointwise_i8_kernel<BN, KB>, (int)smem);
+  const int n_tiles = (p.Cout + BN - 1) / BN, num_kb = (p.K + KB - 1) / KB;
+  const long units = ((p.M + I8_BM - 1) / I8_BM) * n_tiles;
+  const size_t tail = 16 * I8_STAGES + 96 + (size_t)n_tiles * BN * 4;
+  const size_t smem_ring = 1024 + (size_t)I8_STAGES * (I8_BM * I8_BK + BN * I8_BK) + tail;
+  const size_t smem_res = 1024 + (size_t)I8_STAGES * I8_BM * I8_BK + (size_t)num_kb * BN * I8_BK + tail;
+  // resident filter tile: when it fits and there are CTAs for every n-tile
+  p.res = smem_res <= 227 * 1024 && (long)num_sms >= n_tiles && units >= n_tiles ? 1 : 0;
+  const size_t smem = p.res ? smem_res : smem_ring;
+  cudaError_t e = ensure_dyn_smem((const void*)pointwise_i8_kernel<BN, KB>, 227 * 1024);
   if (e != cudaSuccess) return e;
-  const long units = ((p.M + I8_BM - 1) / I8_BM) * ((p.Cout + BN - 1) / BN);
-  const long per_sm = (227 * 1024) / (long)smem < 1 ? 1 : (227 * 1024) / (long)smem;     // resident CTAs per SM (shared memory)
-  long grid = (long)num_sms * (per_sm > 4 ? 4 : per_sm);
+  long per_sm = (227 * 1024) / (long)smem < 1 ? 1 : (227 * 1024) / (long)smem;     // resident CTAs per SM (shared memory)
+  const long tm = 512 / (2 * (BN < 32 ? 32 : BN));                                   // ... and by TMEM columns
+  if (per_sm > tm) per_sm = tm;
+  if (per_sm > 2) per_sm = 2;                                                        // 320 threads each
+  long grid = (long)num_sms * per_sm;
   if (grid > units) grid = units;
+  if (p.res) grid -= grid % n_tiles;
   pointwise_i8_kernel<BN, KB><<<(unsigned)grid, I8_THREADS, smem, st>>>(ta, tb, p);
   return cudaGetLastError();
 }
@@ -293,7 +324,7 @@ __device__ __forceinline__ void transpose4(const uint32_t (&w)[4], uint32_t (&c)
 // (up to) three output rows it belongs to, whose accumulators live in a ring of 3 (stride 1) / 2 (stride 2) slots —
 // the row loop is fully unrolled, so the slots are compile-time registers.
 template <int S>
-__global__ void __launch_bounds__(256) depthwise_u8_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in,
+__global__ void __launch_bounds__(256, 2) depthwise_u8_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in,
                                                            const int* __restrict__ rows32, const int* __restrict__ bias,
                                                            int n, int H, int W, int C, int pad_lo, int relu, int rshift,
                                                            int wrap) {
@@ -319,6 +350,23 @@ __global__ void __launch_bounds__(256) depthwise_u8_kernel(uint8_t* __restrict__
       bs[b] = bias ? __ldg(bias + 4 * c4 + b) : 0;
     }
     int acc[RING][4][4];                      // [slot][channel][output pixel]
+    // The band's input rows are requested PF rows ahead of the row being folded in: with one row at a time every thread
+    // sat out a full L2 / HBM round trip per row (ncu: 3.4 warps stalled on the long scoreboard per issued instruction
+    // at 16 warps per SM).  A row outside the image is the zero padding: its words are zero and contribute nothing.
+    constexpr int PF = S == 1 ? 2 : 1;         // stride 2 reads 9 words per row: a second row in flight would spill
+    uint32_t buf[PF + 1][NW * 4];
+    auto load_row = [&](int q, uint32_t (&px)[NW * 4]) {
+      const int yy = y0 * S + q - pad_lo;
+      const bool ok = yy >= 0 && yy < H;
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(in + ((long)img * H + (ok ? yy : 0)) * W * C) + c4;
+#pragma unroll
+      for (int k = 0; k < NW * 4; ++k) {
+        const int xx = x0 * S + k - pad_lo;
+        px[k] = (ok && k < NPX && xx >= 0 && xx < W) ? __ldg(row + (long)xx * C4) : 0u;
+      }
+    };
+#pragma unroll
+    for (int q = 0; q < PF; ++q) load_row(q, buf[q]);
 #pragma unroll
     for (int q = 0; q < HR; ++q) {
       if (q % S == 0 && q / S < RB) {         // output row q / S starts with this input row: fresh accumulators (+ bias)
@@ -327,15 +375,9 @@ __global__ void __launch_bounds__(256) depthwise_u8_kernel(uint8_t* __restrict__
 #pragma unroll
           for (int j = 0; j < 4; ++j) acc[(q / S) % RING][b][j] = bs[b];
       }
-      const int yy = y0 * S + q - pad_lo;
-      if (yy >= 0 && yy < H) {                // a row outside the image is the zero padding: it contributes nothing
-        const uint32_t* row = reinterpret_cast<const uint32_t*>(in + ((long)img * H + yy) * W * C) + c4;
-        uint32_t px[NW * 4];
-#pragma unroll
-        for (int k = 0; k < NW * 4; ++k) {
-          const int xx = x0 * S + k - pad_lo;
-          px[k] = (k < NPX && xx >= 0 && xx < W) ? __ldg(row + (long)xx * C4) : 0u;
-        }
+      if (q + PF < HR) load_row(q + PF, buf[(q + PF) % (PF + 1)]);
+      {
+        const uint32_t (&px)[NW * 4] = buf[q % (PF + 1)];
         uint32_t ch[NW][4];                   // [group of 4 pixels][channel]
 #pragma unroll
         for (int g = 0; g < NW; ++g) {
@@ -388,19 +430,167 @@ __global__ void __launch_bounds__(256) depthwise_u8_kernel(uint8_t* __restrict__
   }
 }
 
+// ------------------------------------------------------------------------------------------ depthwise, tiled
+// The same arithmetic with the band of input rows staged in shared memory.  The kernel above takes every input word
+// straight from global memory: 16 warps per SM (128 registers for the row ring and the words in flight) cannot cover the
+// round trip, and a third of its instructions are bounds checks and 64-bit addresses (ncu: issue slots 46 %, 3.4 warps
+// stalled on the long scoreboard per issued instruction).  Here one CTA owns a tile of RB output rows x 4 STRIPS output
+// columns x CB channels: all threads copy the (RB-1) S + 3 input rows with cp.async (zero-filled outside the image: the
+// padding), then a thread (4 output pixels x 4 channels, as above) walks down the rows reading its words with
+// immediate-offset shared loads.  The pixel pitch is padded so that the strips of a warp fall into different banks
+// (CB = 32: 10 words, CB = 64: 18 words at stride 2; CB >= 128: a warp is one strip and reads one pixel's channels).
+// Three CTAs per SM overlap one tile's copy with the arithmetic of the others.
+template <int S_, int RB_, int CB_, int STRIPS_>
+struct DtCfg {
+  static constexpr int S = S_, RB = RB_, CB = CB_, STRIPS = STRIPS_;
+  static constexpr int LANES = CB / 4;                 // threads across the channels of a pixel
+  static constexpr int THREADS = STRIPS * LANES;
+  static constexpr int TWO = STRIPS * 4;               // output columns of a tile
+  static constexpr int HR = (RB - 1) * S + 3;          // input rows of a tile
+  static constexpr int BW = (TWO - 1) * S + 3;         // input columns of a tile
+  static constexpr int PITCH = CB == 32 ? 10 : CB == 64 ? 18 : CB / 4;   // words per pixel in shared memory
+  static constexpr int ROWP = BW * PITCH;              // words per row
+  static constexpr int UNIT = CB >= 128 ? 16 : 8;      // bytes per cp.async
+  static constexpr int UPP = CB / UNIT;                // copies per pixel
+  static constexpr int UNITS = HR * BW * UPP;
+  static constexpr size_t SMEM = (size_t)HR * ROWP * 4;
+  static_assert(CB % 32 == 0 && (CB >= 128 || (CB == 32 && S == 1) || (CB == 64 && S == 2)), "pitch table");
+  static_assert(THREADS % 32 == 0 && THREADS <= 256, "whole warps, at most 256 threads");
+};
+
+template <typename Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::S == 1 ? 2 : 3) depthwise_u8_tile_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in,
+                                                                          const int* __restrict__ rows32, const int* __restrict__ bias,
+                                                                          int H, int W, int C, int pad_lo, int relu, int rshift,
+                                                                          int wrap, int bands, int col_tiles, int slabs) {
+  constexpr int S = Cfg::S, RB = Cfg::RB, HR = Cfg::HR, RING = S == 1 ? 3 : 2, NPX = 3 * S + 3, NW = (NPX + 3) / 4;
+  extern __shared__ __align__(16) uint32_t s_tile[];
+  const int Ho = H / S, Wo = W / S;
+  int t = blockIdx.x;
+  const int slab = t % slabs; t /= slabs;
+  const int ct = t % col_tiles; t /= col_tiles;
+  const int band = t % bands;
+  const int img = t / bands;
+  const int cb0 = slab * Cfg::CB, x0t = ct * Cfg::TWO, y0 = band * RB;
+  // ---- copy the tile's input rows (all threads), zero-filled outside the image
+  {
+    const int iy0 = y0 * S - pad_lo, ix0 = x0t * S - pad_lo;
+    const uint8_t* src0 = in + (long)img * H * W * C + cb0;
+    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(s_tile);
+    for (int u = threadIdx.x; u < Cfg::UNITS; u += Cfg::THREADS) {
+      const int cu = u % Cfg::UPP, pr = u / Cfg::UPP, px = pr % Cfg::BW, row = pr / Cfg::BW;
+      const int yy = iy0 + row, xx = ix0 + px;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const uint8_t* src = src0 + ((long)(ok ? yy : 0) * W + (ok ? xx : 0)) * C + cu * Cfg::UNIT;
+      const uint32_t dst = dst0 + (uint32_t)(row * Cfg::ROWP + px * Cfg::PITCH) * 4u + (uint32_t)(cu * Cfg::UNIT);
+      const int bytes = ok ? Cfg::UNIT : 0;       // src-size 0: the destination is filled with zeros
+      if (Cfg::UNIT == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+      else asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // ---- this thread's strip and channels; the taps travel while the copy is in flight
+  const int c4l = threadIdx.x % Cfg::LANES, strip = threadIdx.x / Cfg::LANES;
+  const int c4 = (cb0 >> 2) + c4l, x0 = x0t + strip * 4;
+  int taps[4][3], bs[4];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+#pragma unroll
+    for (int ty = 0; ty < 3; ++ty) taps[b][ty] = __ldg(rows32 + (long)(4 * c4 + b) * 3 + ty);
+    bs[b] = bias ? __ldg(bias + 4 * c4 + b) : 0;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const uint32_t* tp = s_tile + strip * 4 * S * Cfg::PITCH + c4l;
+  const int C4 = C >> 2;
+  int acc[RING][4][4];                        // [slot][channel][output pixel]
+#pragma unroll
+  for (int q = 0; q < HR; ++q) {
+    if (q % S == 0 && q / S < RB) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[(q / S) % RING][b][j] = bs[b];
+    }
+    uint32_t px[NW * 4];
+#pragma unroll
+    for (int k = 0; k < NW * 4; ++k) px[k] = k < NPX ? tp[q * Cfg::ROWP + k * Cfg::PITCH] : 0u;
+    uint32_t ch[NW][4];                       // [group of 4 pixels][channel]
+#pragma unroll
+    for (int g = 0; g < NW; ++g) {
+      const uint32_t w4[4] = {px[4 * g], px[4 * g + 1], px[4 * g + 2], px[4 * g + 3]};
+      transpose4(w4, ch[g]);
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      uint32_t win[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int start = j * S;
+        const uint32_t lo = ch[start >> 2][b], hi = ch[(start >> 2) + 1 < NW ? (start >> 2) + 1 : NW - 1][b];
+        win[j] = (start & 3) ? __funnelshift_r(lo, hi, 8 * (start & 3)) : lo;
+      }
+#pragma unroll
+      for (int ty = 0; ty < 3; ++ty) {
+        if (q - ty >= 0 && (q - ty) % S == 0 && (q - ty) / S < RB) {
+          const int slot = ((q - ty) / S) % RING;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[slot][b][j] = dp4a_u8s8(win[j], taps[b][ty], acc[slot][b][j]);
+        }
+      }
+    }
+    if (q - 2 >= 0 && (q - 2) % S == 0 && (q - 2) / S < RB) {       // output row (q - 2) / S is complete
+      const int o = (q - 2) / S, slot = o % RING, y = y0 + o;
+      if (y < Ho) {
+        uint32_t* orow = reinterpret_cast<uint32_t*>(out + ((long)img * Ho + y) * Wo * C) + c4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (x0 + j >= Wo) break;
+          int v[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) v[b] = acc[slot][b][j];
+          uint32_t w;
+          if (!wrap) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[b] >>= rshift;
+            w = pack4_sat_u8(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { if (relu) v[b] = max(v[b], 0); v[b] >>= rshift; }
+            w = prmt(prmt((uint32_t)v[0], (uint32_t)v[1], 0x0040), prmt((uint32_t)v[2], (uint32_t)v[3], 0x0040), 0x5410);
+          }
+          orow[(long)(x0 + j) * C4] = w;
+        }
+      }
+    }
+  }
+}
+
+template <typename Cfg>
+cudaError_t launch_dw_tile(uint8_t* out, const uint8_t* in, const mnv1_filter* f, int n, int rows, int cols, int c, int pad_lo,
+                           int wrap, cudaStream_t st) {
+  const int Ho = rows / Cfg::S, Wo = cols / Cfg::S;
+  const int bands = (Ho + Cfg::RB - 1) / Cfg::RB, col_tiles = (Wo + Cfg::TWO - 1) / Cfg::TWO, slabs = c / Cfg::CB;
+  const long grid = (long)n * bands * col_tiles * slabs;
+  if (grid <= 0 || grid >= (1L << 31)) return cudaErrorNotSupported;
+  cudaError_t e = ensure_dyn_smem((const void*)depthwise_u8_tile_kernel<Cfg>, (int)Cfg::SMEM);
+  if (e != cudaSuccess) return e;
+  depthwise_u8_tile_kernel<Cfg><<<(unsigned)grid, Cfg::THREADS, Cfg::SMEM, st>>>(
+      out, in, f->w_q32, f->bias_i32, rows, cols, c, pad_lo, f->act != MNV1_ACT_NONE ? 1 : 0, f->rshift, wrap, bands, col_tiles, slabs);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------ stem
 // A thread owns one output pixel and all 32 filters.  Its 27 input bytes are packed into 7 words in the order
 // k = 9*ty + 3*tx + plane — the order in which an interleaved RGB row delivers them: the 9 window bytes of a row are
 // contiguous, so each row costs three aligned 32-bit loads and a funnel shift instead of nine byte loads.  Every filter's
 // 27 s8 values are packed in the same order (api.cu), so one filter costs 7 DP4A.  Planar inputs (the reference's
 // three-plane calling convention) place their bytes in the same order one at a time.  wq: [32][7] words.
-__global__ void __launch_bounds__(128) stem_u8_kernel(uint8_t* __restrict__ out, const StemArgs a, const int* __restrict__ wq,
-                                                      const int* __restrict__ bias, int relu, int rshift, int wrap) {
-  __shared__ int s_w[32 * 7];
-  __shared__ int s_b[32];
-  for (int i = threadIdx.x; i < 32 * 7; i += blockDim.x) s_w[i] = wq[i];
-  if (threadIdx.x < 32) s_b[threadIdx.x] = bias ? bias[threadIdx.x] : 0;
-  __syncthreads();
+// The packed filter bank and the bias travel as a kernel parameter: the DP4As take them straight from the constant bank
+// (from shared memory every DP4A needed a load of its own and the kernel spent half its issue slots on them).
+struct StemU8Consts { int w[32 * 7]; int b[32]; };
+__global__ void __launch_bounds__(128) stem_u8_kernel(uint8_t* __restrict__ out, const __grid_constant__ StemArgs a,
+                                                      const __grid_constant__ StemU8Consts cw, int relu, int rshift, int wrap) {
   const int Ho = a.rows / a.stride, Wo = a.cols / a.stride;
   const long total = (long)a.n * Ho * Wo;
   const bool interleaved = a.pix_stride == 3 && a.g == a.r + 1 && a.b == a.r + 2 && (a.cols * 3) % 4 == 0 && a.img_stride % 4 == 0 &&
@@ -464,9 +654,9 @@ __global__ void __launch_bounds__(128) stem_u8_kernel(uint8_t* __restrict__ out,
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int f = 4 * f4 + b;
-        int acc = s_b[f];
+        int acc = cw.b[f];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) acc = dp4a_u8s8(pk[k], s_w[f * 7 + k], acc);
+        for (int t = 0; t < 7; ++t) acc = dp4a_u8s8(pk[t], cw.w[f * 7 + t], acc);
         v[b] = acc;
       }
       if (!wrap) {
@@ -571,6 +761,20 @@ cudaError_t launch_depthwise_u8(uint8_t* out, const uint8_t* in, const mnv1_filt
                                 int c, int pad_lo, int wrap, cudaStream_t st) {
   if (c % 4 || !f->w_q32) return cudaErrorNotSupported;
   if (n <= 0) return cudaSuccess;
+  // 128 channels and more go through shared memory (32 / 64 channels measured faster on the direct kernel: 89 vs 99 us on
+  // layer 2, 78 vs 82 us on layer 4 — four strips of a warp share the copy's 8-byte granularity and the padded pitch)
+  if ((reinterpret_cast<uintptr_t>(in) & 15) == 0 && rows % stride == 0 && cols % stride == 0) {
+    const int wo = cols / stride;
+    if (stride == 1) {
+      if (c % 512 == 0 && wo <= 8) return launch_dw_tile<DtCfg<1, 7, 512, 2>>(out, in, f, n, rows, cols, c, pad_lo, wrap, st);
+      if (c % 256 == 0 && wo <= 16) return launch_dw_tile<DtCfg<1, 7, 256, 4>>(out, in, f, n, rows, cols, c, pad_lo, wrap, st);
+      if (c % 128 == 0) return launch_dw_tile<DtCfg<1, 7, 128, 7>>(out, in, f, n, rows, cols, c, pad_lo, wrap, st);
+    } else if (stride == 2) {
+      if (c % 512 == 0 && wo <= 8) return launch_dw_tile<DtCfg<2, 4, 512, 2>>(out, in, f, n, rows, cols, c, pad_lo, wrap, st);
+      if (c % 128 == 0 && wo <= 16) return launch_dw_tile<DtCfg<2, 4, 128, 4>>(out, in, f, n, rows, cols, c, pad_lo, wrap, st);
+      if (c % 128 == 0) return launch_dw_tile<DtCfg<2, 4, 128, 7>>(out, in, f, n, rows, cols, c, pad_lo, wrap, st);
+    }
+  }
   const long total = (long)n * ((rows / stride + 6) / 7) * ((cols / stride + 3) / 4) * (c / 4);
   const int relu = f->act != MNV1_ACT_NONE ? 1 : 0;
   if (stride == 1)
@@ -584,7 +788,11 @@ cudaError_t launch_stem_u8(uint8_t* out, const StemArgs& a, const mnv1_filter* f
   if (a.cout != 32 || !f->w_q32) return cudaErrorNotSupported;
   if (a.n <= 0) return cudaSuccess;
   const long total = (long)a.n * (a.rows / a.stride) * (a.cols / a.stride);
-  stem_u8_kernel<<<grid_for(total, 128), 128, 0, st>>>(out, a, f->w_q32, f->bias_i32, f->act != MNV1_ACT_NONE ? 1 : 0, f->rshift, wrap);
+  if (f->h_q32.size() != 32 * 7) return cudaErrorNotSupported;
+  StemU8Consts k;
+  for (int i = 0; i < 32 * 7; ++i) k.w[i] = f->h_q32[i];
+  for (int i = 0; i < 32; ++i) k.b[i] = f->h_bias.empty() ? 0 : f->h_bias[i];
+  stem_u8_kernel<<<grid_for(total, 128), 128, 0, st>>>(out, a, k, f->act != MNV1_ACT_NONE ? 1 : 0, f->rshift, wrap);
   return cudaGetLastError();
 }
 
