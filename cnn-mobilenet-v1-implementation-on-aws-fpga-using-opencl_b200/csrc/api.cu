@@ -630,7 +630,7 @@ static cudaError_t run_stem(mnv1_ctx* ctx, void* out, const uint8_t* r, const ui
   ctx->launches++;
   if (ctx->dtype == MNV1_U8) {
     ctx->last_kernel = "stem_u8_kernel";
-    return mnv1::launch_stem_u8((uint8_t*)out, a, f, ctx->u8_wrap, ctx->stream);
+    return mnv1::launch_stem_u8((uint8_t*)out, a, f, ctx->u8_wrap, ctx->num_sms, ctx->stream, &ctx->last_kernel);
   }
   if (ctx->dtype == MNV1_BF16 && f->prepared && f->prep_scale == ctx->in_scale && f->prep_bias == ctx->in_bias) {
     ctx->err.clear();

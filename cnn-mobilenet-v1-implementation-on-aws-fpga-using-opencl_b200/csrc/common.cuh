@@ -205,7 +205,8 @@ cudaError_t launch_pointwise_i8(uint8_t* out, const uint8_t* in, const mnv1_filt
                                 int num_sms, cudaStream_t st, std::string* err);
 cudaError_t launch_depthwise_u8(uint8_t* out, const uint8_t* in, const mnv1_filter* f, int n, int rows, int cols, int stride,
                                 int c, int pad_lo, int wrap, cudaStream_t st);
-cudaError_t launch_stem_u8(uint8_t* out, const StemArgs& a, const mnv1_filter* f, int wrap, cudaStream_t st);
+cudaError_t launch_stem_u8(uint8_t* out, const StemArgs& a, const mnv1_filter* f, int wrap, int num_sms, cudaStream_t st,
+                           const char** kernel_name = nullptr);
 cudaError_t launch_pool_u8(uint8_t* out, const uint8_t* in, int n, int hw, int c, int wrap, cudaStream_t st);
 // dir 0: planar host order (u8 or float values) -> NHWC u8; dir 1: NHWC u8 -> planar (u8 or float)
 cudaError_t launch_u8_layout(int dir, void* out, const void* in, bool host_is_u8, int n, int c, int hw, cudaStream_t st);

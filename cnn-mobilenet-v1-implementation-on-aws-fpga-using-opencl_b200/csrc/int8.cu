@@ -674,6 +674,176 @@ __global__ void __launch_bounds__(128) stem_u8_kernel(uint8_t* __restrict__ out,
   }
 }
 
+// ------------------------------------------------------------------------------------------ stem on the tensor cores
+// DP4A issues at a quarter of the FP32 rate on this part (one warp instruction every four cycles per scheduler), so the
+// 224 DP4As per output pixel above cost 80 us per 256 images whatever else the kernel does.  This is stem_rows.cu for
+// bytes: a tile is one output row of one image; a producer thread lands the tile's three input rows (contiguous in the
+// interleaved image) in a ring slot with one bulk copy; the gather threads (thread = output column) read the nine window
+// bytes of each row with three aligned shared loads + a funnel shift and write them AS THEY ARE into the 32-byte-swizzled
+// K-major A operand (k = 8 row + j for window bytes j < 8, k = 24 + row for byte 8: no byte ever crosses a word; the
+// filter bank is permuted to match); ONE tcgen05.mma kind::i8 (M 128, N 32, K 32) per tile; the epilogue warps add the
+// bias, shift, saturate and store 32 bytes per pixel with one 256-bit store.  Zero padding: missing rows are tile-uniform,
+// missing columns touch the first / last thread.
+constexpr int SI_THREADS = 320;   // 4 gather + 4 epilogue + MMA/TMEM + producer warps
+constexpr int SI_NI = 8;          // input ring depth
+constexpr int SI_NA = 4;          // A tiles / accumulators in flight
+constexpr int SI_LEAD = 16;       // bytes before row 0 in a slot (column -1 of the REF padding)
+constexpr uint32_t SI_A_BYTES = 128 * 32, SI_B_BYTES = 32 * 32;
+struct StemI8Params {
+  const uint8_t* img;    // interleaved RGB, n x rows x cols x 3
+  uint8_t* out;          // n x orows x ocols x 32
+  long img_stride;
+  int rows, cols, orows, ocols, pad_lo, tiles, slot_bytes, relu, rshift, wrap;
+  uint32_t b[32][8];     // filter bank: [filter][k / 4] words of 4 s8 in the A operand's k order
+  int bias[32];
+};
+
+__global__ void __launch_bounds__(SI_THREADS, 3) stem_i8_rows_kernel(const __grid_constant__ StemI8Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem;                               // NA x 4 KB
+  const uint32_t sB = smem + SI_NA * SI_A_BYTES;          // 1 KB
+  const uint32_t bars = sB + SI_B_BYTES;                  // a_full[NA] mma_done[NA] tmem_free[NA] in_full[NI] in_empty[NI]
+  const uint32_t a_full = bars, mma_done = a_full + 8 * SI_NA, tmem_free = mma_done + 8 * SI_NA,
+                 in_full = tmem_free + 8 * SI_NA, in_empty = in_full + 8 * SI_NI;
+  const uint32_t tmem_slot = in_empty + 8 * SI_NI;
+  const uint32_t sIn = bars + 256;                        // NI slots of slot_bytes
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 32) {                                         // B tile: filter `tid`, 32-byte swizzle (16-byte chunk ^= bit 2 of the row)
+    const uint32_t row = sB + (uint32_t)tid * 32u, sw = (uint32_t)(tid >> 2) & 1u;
+    sts128(row + ((0u ^ sw) << 4), p.b[tid][0], p.b[tid][1], p.b[tid][2], p.b[tid][3]);
+    sts128(row + ((1u ^ sw) << 4), p.b[tid][4], p.b[tid][5], p.b[tid][6], p.b[tid][7]);
+  }
+  if (tid == 0) {
+    for (int b = 0; b < SI_NA; ++b) { mbar_init(a_full + 8 * b, 128); mbar_init(mma_done + 8 * b, 1); mbar_init(tmem_free + 8 * b, 4); }
+    for (int s = 0; s < SI_NI; ++s) { mbar_init(in_full + 8 * s, 1); mbar_init(in_empty + 8 * s, 4); }
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, (uint32_t)(SI_NA * 32));
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = lds32(tmem_slot);
+  const int Wo = p.ocols, Ho = p.orows, H = p.rows, RB = p.cols * 3;
+  const int tiles = p.tiles;
+
+  if (warp < 4) {
+    // ======================= gather warps (thread = output column) =======================
+    const int ox = tid;
+    const int start = SI_LEAD + 6 * ox - 3 * p.pad_lo;      // byte offset of the window in a slot row
+    const uint32_t sh8 = (uint32_t)(start & 3) * 8;
+    const uint32_t col_off = (uint32_t)(start & ~3);
+    const bool pad_left = 2 * ox - p.pad_lo < 0, pad_right = 2 * ox - p.pad_lo + 2 >= p.cols;
+    const int oy_step = (int)(gridDim.x % (unsigned)Ho);
+    int oy = (int)(blockIdx.x % (unsigned)Ho);
+    const uint32_t sw = (uint32_t)(tid >> 2) & 1u;
+    int i = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+      const int slot = i % SI_NI, kin = i / SI_NI, buf = i % SI_NA, k = i / SI_NA;
+      mbar_wait(in_full + 8 * slot, (uint32_t)kin & 1u);
+      uint32_t a[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = 0u;
+      if (ox < Wo) {
+        const uint32_t base = sIn + (uint32_t)slot * (uint32_t)p.slot_bytes + col_off;
+        const int iy0 = 2 * oy - p.pad_lo;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          if (iy0 + r < 0 || iy0 + r >= H) continue;        // a row outside the image is the zero padding (tile-uniform)
+          const uint32_t w0 = lds32(base + r * RB), w1 = lds32(base + r * RB + 4), w2 = lds32(base + r * RB + 8);
+          uint32_t b0 = __funnelshift_r(w0, w1, sh8), b1 = __funnelshift_r(w1, w2, sh8), e8 = (w2 >> sh8) & 0xffu;
+          if (pad_left) b0 &= 0xff000000u;                  // window bytes 0..2 = column -1
+          if (pad_right) { b1 &= 0x0000ffffu; e8 = 0u; }    // window bytes 6..8 = column `cols`
+          a[2 * r] = b0; a[2 * r + 1] = b1;
+          a[6] |= e8 << (8 * r);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(in_empty + 8 * slot);      // the slot's bytes are in registers
+      oy += oy_step;
+      if (oy >= Ho) oy -= Ho;
+      if (k > 0) mbar_wait(mma_done + 8 * buf, (uint32_t)(k - 1) & 1u);   // A[buf] was read by the MMA of tile i - NA
+      const uint32_t arow = sA + (uint32_t)buf * SI_A_BYTES + (uint32_t)tid * 32u;
+      sts128(arow + ((0u ^ sw) << 4), a[0], a[1], a[2], a[3]);
+      sts128(arow + ((1u ^ sw) << 4), a[4], a[5], a[6], a[7]);
+      fence_proxy_async();
+      mbar_arrive(a_full + 8 * buf);
+    }
+  } else if (warp < 8) {
+    // ======================= epilogue warps =======================
+    const int q = warp & 3, col = q * 32 + lane;
+    int i = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+      const int buf = i % SI_NA, k = i / SI_NA;
+      mbar_wait(mma_done + 8 * buf, (uint32_t)k & 1u);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 32), v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_free + 8 * buf);
+      if (col >= Wo) continue;
+      int x[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = (int)v[j] + p.bias[j];
+      uint32_t w[8];
+      if (!p.wrap) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] >>= p.rshift;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) w[j] = pack4_sat_u8(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { if (p.relu) x[j] = max(x[j], 0); x[j] >>= p.rshift; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          w[j] = prmt(prmt((uint32_t)x[4 * j], (uint32_t)x[4 * j + 1], 0x0040), prmt((uint32_t)x[4 * j + 2], (uint32_t)x[4 * j + 3], 0x0040), 0x5410);
+      }
+      uint8_t* o = p.out + ((long)t * Wo + col) * 32;
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                   "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+    }
+  } else if (warp == 8) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_u8s8_m128(32);
+      const uint64_t descB = umma_desc_kmajor<32>(sB);
+      int i = 0;
+      for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+        const int buf = i % SI_NA, k = i / SI_NA;
+        if (k > 0) mbar_wait(tmem_free + 8 * buf, (uint32_t)(k - 1) & 1u);
+        mbar_wait(a_full + 8 * buf, (uint32_t)k & 1u);
+        tc_fence_after();
+        umma_i8(tmem_base + (uint32_t)(buf * 32), umma_desc_kmajor<32>(sA + (uint32_t)buf * SI_A_BYTES), descB, idesc, 0u);
+        umma_commit(mma_done + 8 * buf);
+      }
+    }
+  } else if (lane == 0) {
+    // ======================= producer: one bulk copy (the tile's input rows) per tile ==========
+    int i = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++i) {
+      const int slot = i % SI_NI, kin = i / SI_NI;
+      if (kin > 0) mbar_wait(in_empty + 8 * slot, (uint32_t)(kin - 1) & 1u);
+      const int img = t / Ho, oy = t - img * Ho;
+      const int iy0 = 2 * oy - p.pad_lo;
+      const int r_lo = iy0 < 0 ? 0 : iy0, r_hi = iy0 + 3 > H ? H : iy0 + 3;
+      const uint32_t bytes = (uint32_t)((r_hi - r_lo) * RB);
+      const uint32_t dst = sIn + (uint32_t)slot * (uint32_t)p.slot_bytes + SI_LEAD + (uint32_t)((r_lo - iy0) * RB);
+      mbar_expect_tx(in_full + 8 * slot, bytes);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(p.img + (long)img * p.img_stride + (long)r_lo * RB), "r"(bytes), "r"(in_full + 8 * slot) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)(SI_NA * 32));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ pool, layout, logits
 // kernel.cl:116-131: integer sum of the f*f values of a channel, truncating division.
 __global__ void pool_u8_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in, int n, int hw, int c, int wrap) {
@@ -784,11 +954,44 @@ cudaError_t launch_depthwise_u8(uint8_t* out, const uint8_t* in, const mnv1_filt
   return cudaGetLastError();
 }
 
-cudaError_t launch_stem_u8(uint8_t* out, const StemArgs& a, const mnv1_filter* f, int wrap, cudaStream_t st) {
+cudaError_t launch_stem_u8(uint8_t* out, const StemArgs& a, const mnv1_filter* f, int wrap, int num_sms, cudaStream_t st,
+                           const char** kernel_name) {
   if (a.cout != 32 || !f->w_q32) return cudaErrorNotSupported;
   if (a.n <= 0) return cudaSuccess;
   const long total = (long)a.n * (a.rows / a.stride) * (a.cols / a.stride);
   if (f->h_q32.size() != 32 * 7) return cudaErrorNotSupported;
+  const bool il = a.pix_stride == 3 && a.g == a.r + 1 && a.b == a.r + 2;
+  const int rb = a.cols * 3;
+  if (il && a.stride == 2 && !(a.rows & 1) && !(a.cols & 1) && a.cols / 2 <= 128 && rb % 16 == 0 && a.img_stride % 16 == 0 &&
+      (reinterpret_cast<uintptr_t>(a.r) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0 && f->rshift < 32 &&
+      (long)a.n * (a.rows / 2) < (1L << 31)) {
+    StemI8Params p{};
+    p.img = a.r; p.out = out; p.img_stride = a.img_stride; p.rows = a.rows; p.cols = a.cols; p.orows = a.rows / 2; p.ocols = a.cols / 2;
+    p.pad_lo = a.pad_lo; p.tiles = a.n * p.orows; p.relu = f->act != MNV1_ACT_NONE ? 1 : 0; p.rshift = f->rshift; p.wrap = wrap;
+    p.slot_bytes = (SI_LEAD + 3 * rb + 16 + 127) & ~127;
+    // h_q32 holds filter o's 27 s8 values at byte 9 ty + 3 tx + plane; the A operand's order is k = 8 ty + j (j = 3 tx + plane < 8),
+    // k = 24 + ty for j = 8
+    for (int o = 0; o < 32; ++o) {
+      for (int w = 0; w < 8; ++w) p.b[o][w] = 0u;
+      for (int ty = 0; ty < 3; ++ty)
+        for (int j = 0; j < 9; ++j) {
+          const int src = 9 * ty + j, k = j < 8 ? 8 * ty + j : 24 + ty;
+          const uint32_t v = ((uint32_t)f->h_q32[o * 7 + (src >> 2)] >> (8 * (src & 3))) & 0xffu;
+          p.b[o][k >> 2] |= v << (8 * (k & 3));
+        }
+      p.bias[o] = f->h_bias.empty() ? 0 : f->h_bias[o];
+    }
+    const size_t smem = 1024 + SI_NA * SI_A_BYTES + SI_B_BYTES + 256 + (size_t)SI_NI * p.slot_bytes;
+    if (smem <= 75 * 1024) {   // 3 CTAs per SM
+      cudaError_t e = ensure_dyn_smem((const void*)stem_i8_rows_kernel, 75 * 1024);
+      if (e != cudaSuccess) return e;
+      long grid = (long)num_sms * 3;
+      if (grid > p.tiles) grid = p.tiles;
+      if (kernel_name) *kernel_name = "stem_i8_rows_kernel";
+      stem_i8_rows_kernel<<<(unsigned)grid, SI_THREADS, smem, st>>>(p);
+      return cudaGetLastError();
+    }
+  }
   StemU8Consts k;
   for (int i = 0; i < 32 * 7; ++i) k.w[i] = f->h_q32[i];
   for (int i = 0; i < 32; ++i) k.b[i] = f->h_bias.empty() ? 0 : f->h_bias[i];

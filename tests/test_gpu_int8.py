@@ -90,11 +90,12 @@ def test_stem_u8(ictx, mn, oracle_mod, pad):
     f = ictx.filter(mn.CONVOLUTE, w.astype(np.float32), 3, 32, act=mn.ACT_RELU)
     out = ictx.malloc(n, 32, 112, 112)
     ictx.convolute_rgb(out, ictx.upload_u8(img), f, 224, 224, 3, 2, 32)
-    assert ictx.last_kernel_name == "stem_u8_kernel"
+    assert ictx.last_kernel_name == "stem_i8_rows_kernel"      # interleaved payload: tcgen05 kind::i8
     assert np.array_equal(ictx.download_planar_u8(out), want)
     planes = [ictx.upload_u8(np.ascontiguousarray(img[..., k])) for k in range(3)]
     out2 = ictx.malloc(n, 32, 112, 112)
     ictx.convolute(out2, planes[0], planes[1], planes[2], f, 224, 224, 3, 2, 32)
+    assert ictx.last_kernel_name == "stem_u8_kernel"           # three planes: DP4A
     assert np.array_equal(ictx.download_planar_u8(out2), want)
     ictx.set_pad_mode(mn.PAD_REF)
 
