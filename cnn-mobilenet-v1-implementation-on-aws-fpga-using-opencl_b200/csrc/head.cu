@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) pool_kernel(TO* __restrict__ out, const T
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (c0 < c) {
     const T* p = in + (long)img * hw * c + c0;
-#pragma unroll 4
+#pragma unroll 13   // hw = 49: 12 or 13 rows per phase, all of a thread's loads in flight at once (same summation order)
     for (int i = ph; i < hw; i += 4) {
       if constexpr (sizeof(T) == 2) {
         const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (long)i * c));
