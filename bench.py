@@ -514,19 +514,24 @@ def run_ours(args):
                 return [float(t.item()) for t in tw_ranks], counts
 
             _, link = h2d_ceiling(ctx, torch, dev, batch * IMG_BYTES, world, dist)
-            # calibration pass (untimed for the record): shares from the link rates, then from the rates the ranks reached
-            t_cal, c_cal = weighted_e2e(link, 1)
-            reached = [c / t for c, t in zip(c_cal, t_cal)]
-            tw_ranks, counts = weighted_e2e(reached, 3)
-            e2e_equal_value, e2e_equal_ranks = e2e_value, e2e_ranks
-            e2e_value, e2e_ranks = world * batch * ke / max(tw_ranks), tw_ranks
-            shard_info = {"images_per_rank": counts, "link_gbs": link, "calibration_pass_images_per_rank": c_cal,
-                          "how": "global batch cut by mnv1_dp_shard_weighted: first in proportion to each rank's pinned H2D "
-                                 "rate with all ranks copying, then (one untimed calibration pass of `steps` steps) in proportion "
-                                 "to the images/s each rank reached; the gather block keeps its world x batch rows "
-                                 "(mnv1_gather_set_rows)"}
-            if ctx.gather_active():
-                ctx.gather_set_rows(rank * batch, batch)
+            if max(link) < 1.05 * min(link):
+                # the links are even (every rank saw the same list): equal shards are the proportional shards
+                shard_info = {"images_per_rank": [batch] * world, "link_gbs": link,
+                              "how": "the ranks' pinned H2D rates with all ranks copying are within 5 %: equal shards"}
+            else:
+                # calibration pass (untimed for the record): shares from the link rates, then from the rates the ranks reached
+                t_cal, c_cal = weighted_e2e(link, 1)
+                reached = [c / t for c, t in zip(c_cal, t_cal)] if max(t_cal) > 1.03 * min(t_cal) else link
+                tw_ranks, counts = weighted_e2e(reached, 3)
+                e2e_equal_value, e2e_equal_ranks = e2e_value, e2e_ranks
+                e2e_value, e2e_ranks = world * batch * ke / max(tw_ranks), tw_ranks
+                shard_info = {"images_per_rank": counts, "link_gbs": link, "calibration_pass_images_per_rank": c_cal,
+                              "how": "global batch cut by mnv1_dp_shard_weighted: first in proportion to each rank's pinned H2D "
+                                     "rate with all ranks copying, then (one untimed calibration pass of `steps` steps) in "
+                                     "proportion to the images/s each rank reached; the gather block keeps its world x batch "
+                                     "rows (mnv1_gather_set_rows)"}
+                if ctx.gather_active():
+                    ctx.gather_set_rows(rank * batch, batch)
         # one blocking call (no overlap) for reference, and a consistency check of the pipelined outputs
         t0 = time.perf_counter()
         for _ in range(5):
@@ -593,7 +598,7 @@ def run_ours(args):
                        "d2h_bytes_per_step": batch * 1000 * 4 + batch * 8, "bytes_are": "per rank, mean over ranks",
                        "steps": ke,
                        "api": "mnv1_forward_submit/_wait (C-ABI, pinned host buffers, 3 batches in flight)"
-                              + ("" if world == 1 else "; shards of the global batch in proportion to the ranks' H2D rates"),
+                              + ("" if e2e_equal_value is None else "; shards of the global batch in proportion to the ranks' H2D rates"),
                        "timing": "wall clock, median of 3 repetitions of `steps` steps, max over ranks",
                        "blocking_call_value": round(e2e_blocking, 1),
                        "step_ms_per_rank": [round(t / ke * 1e3, 3) for t in e2e_ranks],
