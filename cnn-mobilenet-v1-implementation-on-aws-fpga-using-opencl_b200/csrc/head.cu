@@ -165,8 +165,14 @@ __global__ void __launch_bounds__(256, 1) fc_kernel(float* __restrict__ out, con
 // The four warps of a CTA split the contraction (k/4 each, summed in a fixed order through shared memory):
 // 512 CTAs of short dependent chains instead of 128 long ones — the kernel is latency-, not math-bound.
 // The legacy mma.sync path is deliberate: M = 256 is two tcgen05 tiles — not enough CTAs to matter.
-constexpr int FCM_NT = 4;        // 8-class fragments per warp (a CTA owns 16 images x 32 classes)
-constexpr int FCM_WARPS = 4;     // warps per CTA = k-splits
+#ifndef MNV1_FCM_NT
+#define MNV1_FCM_NT 4
+#endif
+#ifndef MNV1_FCM_WARPS
+#define MNV1_FCM_WARPS 4
+#endif
+constexpr int FCM_NT = MNV1_FCM_NT;        // 8-class fragments per warp (a CTA owns 16 images x 32 classes)
+constexpr int FCM_WARPS = MNV1_FCM_WARPS;     // warps per CTA = k-splits
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -183,13 +189,17 @@ __device__ __forceinline__ void split3(float x0, float x1, uint32_t& hi, uint32_
   mid = (m0 >> 16) | m1;
   lo = (__float_as_uint(s0) >> 16) | (__float_as_uint(s1) & 0xffff0000u);
 }
-// FCM_DEPTH k-steps of operand loads are kept in flight per warp: a warp's share of the contraction is only k/4 = 256 = 8
-// steps of 32, and with one step of prefetch every step exposed an L2 round trip (the kernel is latency-bound).
+// FCM_DEPTH k-steps of operand loads are kept in flight per warp.  Measured inside the graph (tools/prefix_times.py, head =
+// pool + FC + softmax): depth 4 at 227 registers = two CTAs per SM, the 512 CTAs need a second, mostly empty wave: 21.5 us;
+// depth 1 under a 128-register bound = four CTAs per SM, one wave: 19.4 us (depth 2 at 128 registers spills: 21.6 us).
 #ifndef MNV1_FCM_DEPTH
-#define MNV1_FCM_DEPTH 4
+#define MNV1_FCM_DEPTH 1
 #endif
 constexpr int FCM_DEPTH = MNV1_FCM_DEPTH;
-__global__ void __launch_bounds__(FCM_WARPS * 32) fc_mma_kernel(float* __restrict__ out, const float* __restrict__ pooled,
+#ifndef MNV1_FCM_MINB
+#define MNV1_FCM_MINB 4
+#endif
+__global__ void __launch_bounds__(FCM_WARPS * 32, MNV1_FCM_MINB) fc_mma_kernel(float* __restrict__ out, const float* __restrict__ pooled,
                                                                 const bf16* __restrict__ w, const float* __restrict__ bias,
                                                                 int n, int k, int classes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;

@@ -296,7 +296,12 @@ cudaError_t encode_box(CUtensorMap* map, const void* base, uint64_t rows, uint64
 // cudaErrorNotSupported (nothing launched) when the shape has no cluster variant.
 cudaError_t launch_pointwise_pair(bf16* out, const bf16* in, const mnv1_filter* f, long m, int k, int cout, int num_sms,
                                 cudaStream_t st, std::string* err) {
-  if (switches().no_pair || !f->w_bf16 || cout % 256 || k % MC_BK || k < 256 || cout > 1024 || num_sms < 2) return cudaErrorNotSupported;
+  // K = 256 (layer 13) stays on the single-CTA kernel: with four k-blocks per tile the pair's cluster hand-shakes cost more
+  // than the halved filter traffic saves (in the graph 16.9 vs 18.7 us; MNV1_PAIR_MIN_K=256 brings the pair kernel back)
+#ifndef MNV1_PAIR_MIN_K
+#define MNV1_PAIR_MIN_K 512
+#endif
+  if (switches().no_pair || !f->w_bf16 || cout % 256 || k % MC_BK || k < MNV1_PAIR_MIN_K || cout > 1024 || num_sms < 2) return cudaErrorNotSupported;
   if (m <= 0) return cudaSuccess;
   CUtensorMap ta, tb, tb64, to;
   cudaError_t e = encode_box(&ta, in, (uint64_t)m, (uint64_t)k, 128, err);

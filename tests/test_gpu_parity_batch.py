@@ -44,7 +44,7 @@ def _net_ctx(mn, dtype, w, sc, sh):
     (512, 512, 14, 256),    # layer 15 at the benched batch: M = 50176 -> 392 units on 74 pairs, 6 rounds, ragged last
     (1024, 1024, 7, 256),   # layer 27: M = 12544 -> 49 m-pairs x 4 n-tiles = 196 units, 16 k-blocks per tile
     (512, 1024, 7, 256),    # layer 25
-    (256, 512, 14, 256),    # layer 13 (K = 256: 4 k-blocks, ring wraps every tile)
+    (256, 512, 14, 256),    # layer 13 (K = 256: the single-CTA tcgen05 kernel, 4 k-blocks, ring wraps every tile)
     (512, 512, 14, 37),     # ragged M: 7252 rows -> 57 m-tiles (odd), last tile 84 rows
     (512, 512, 14, 101),    # 19796 rows -> 155 m-tiles: odd tile count, units % clusters != 0, >= 2 rounds
 ])
@@ -60,7 +60,7 @@ def test_pointwise_pair_many_rounds(mn, oracle_mod, cin, cout, h, n):
     xin = ctx.upload_planar(x)
     out = ctx.malloc(n, cout, h, h)
     ctx.pointwise(out, xin, f, h, h, cin, cout)
-    assert ctx.last_kernel_name == "pointwise_pair_kernel"
+    assert ctx.last_kernel_name == ("pointwise_pair_kernel" if cin >= 512 else "pointwise_tc_kernel")   # K = 256: single CTA
     got = ctx.download_planar(out)
     assert rel_err(got, want) <= BF16_TOL
     # and twice more on the same context: a second launch must not depend on left-over barrier state
@@ -88,7 +88,7 @@ def test_kat_pointwise_pair_three_way(mn, oracle_mod, cin, cout, h, n):
     xin = ctx.upload_planar(x.astype(np.float32))
     out = ctx.malloc(n, cout, h, h)
     ctx.pointwise(out, xin, f, h, h, cin, cout)
-    assert ctx.last_kernel_name == "pointwise_pair_kernel"
+    assert ctx.last_kernel_name == ("pointwise_pair_kernel" if cin >= 512 else "pointwise_tc_kernel")
     assert np.array_equal(ctx.download_planar(out), want)
     ctx.close()
 
