@@ -209,6 +209,9 @@ def test_dp_shard_weighted_apportions_the_batch():
                 assert cover == list(range(n))
                 for r in range(world):
                     assert abs(counts[r] - n * w[r] / sum(w)) < 1.0 + 1e-6
+                for r in range(world):                      # the Python mirror agrees with the C-ABI
+                    a, b = shard.weighted_range(n, r, world, w)
+                    assert (a, b - a) == mn.dp_shard_weighted(n, r, world, w)
             for r in range(world):
                 assert mn.dp_shard_weighted(n, r, world, [3.0] * world) == mn.dp_shard(n, r, world)
                 assert mn.dp_shard_weighted(n, r, world, None) == mn.dp_shard(n, r, world)

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, n_global, q):
+def _worker(rank, world, port, n_global, q, weights=None):
     for p in (ROOT, os.path.join(ROOT, "oracle")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -22,24 +22,25 @@ def _worker(rank, world, port, n_global, q):
     from mnv1_b200 import shard, synth
     import oracle
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    a, b = shard.shard_range(n_global, rank, world)
+    a, b = shard.weighted_range(n_global, rank, world, weights)
     w = synth.weights()
     sc, sh = synth.batchnorm()
     local, _ = oracle.forward(synth.images(b - a, first=a), w, sc, sh)  # images indexed globally
-    full = shard.gather_logits(torch.from_numpy(local), n_global)
+    full = shard.gather_logits(torch.from_numpy(local), n_global, weights=weights)
     if rank == 0:
         q.put(full.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_global", [4, 3])
-def test_two_rank_shard_and_gather(n_global, oracle_mod, synth_net):
+@pytest.mark.parametrize("n_global,weights", [(4, None), (3, None), (4, [22.7, 37.9])])
+def test_two_rank_shard_and_gather(n_global, weights, oracle_mod, synth_net):
+    """equal shards, a ragged batch, and shards in proportion to the ranks' host links (1 + 3 images)"""
     import socket
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_global, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_global, q, weights)) for r in range(2)]
     for p in procs:
         p.start()
     full = q.get(timeout=240)
