@@ -856,6 +856,32 @@ __global__ void pool_u8_kernel(uint8_t* __restrict__ out, const uint8_t* __restr
     out[i] = (uint8_t)store_u8(sum / hw, wrap);
   }
 }
+// Four channels per thread (c % 4 == 0, hw <= 257): one 32-bit load per pixel, the four byte sums carried in two words of
+// two 16-bit lanes each (hw * 255 < 65536), all of a thread's loads of a batch of 7 pixels in flight at once.
+__global__ void __launch_bounds__(128) pool_u8_vec_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in, int n, int hw,
+                                                          int c, int wrap) {
+  const int c4n = c >> 2;
+  const long total = (long)n * c4n;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const long img = i / c4n;
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(in + img * hw * c) + c4;
+    uint32_t s02 = 0u, s13 = 0u;                 // (ch0, ch2) and (ch1, ch3) as 16-bit lanes
+    int px = 0;
+    for (; px + 7 <= hw; px += 7) {
+      uint32_t w[7];
+#pragma unroll
+      for (int k = 0; k < 7; ++k) w[k] = __ldg(p + (long)(px + k) * c4n);
+#pragma unroll
+      for (int k = 0; k < 7; ++k) { s02 += w[k] & 0x00ff00ffu; s13 += (w[k] >> 8) & 0x00ff00ffu; }
+    }
+    for (; px < hw; ++px) { const uint32_t w = __ldg(p + (long)px * c4n); s02 += w & 0x00ff00ffu; s13 += (w >> 8) & 0x00ff00ffu; }
+    const int s0 = (int)(s02 & 0xffffu), s2 = (int)(s02 >> 16), s1 = (int)(s13 & 0xffffu), s3 = (int)(s13 >> 16);
+    const uint32_t r = store_u8(s0 / hw, wrap) | (store_u8(s1 / hw, wrap) << 8) | (store_u8(s2 / hw, wrap) << 16) |
+                       (store_u8(s3 / hw, wrap) << 24);
+    reinterpret_cast<uint32_t*>(out + img * c)[c4] = r;
+  }
+}
 template <typename TI>
 __global__ void nchw_to_nhwc_u8_kernel(uint8_t* __restrict__ out, const TI* __restrict__ in, int n, int c, int hw) {
   const long total = (long)n * c * hw;
@@ -1001,7 +1027,10 @@ cudaError_t launch_stem_u8(uint8_t* out, const StemArgs& a, const mnv1_filter* f
 
 cudaError_t launch_pool_u8(uint8_t* out, const uint8_t* in, int n, int hw, int c, int wrap, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  pool_u8_kernel<<<grid_for((long)n * c, 256), 256, 0, st>>>(out, in, n, hw, c, wrap);
+  if (c % 4 == 0 && hw <= 257 && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 3) == 0)
+    pool_u8_vec_kernel<<<grid_for((long)n * (c / 4), 128), 128, 0, st>>>(out, in, n, hw, c, wrap);
+  else
+    pool_u8_kernel<<<grid_for((long)n * c, 256), 256, 0, st>>>(out, in, n, hw, c, wrap);
   return cudaGetLastError();
 }
 
