@@ -54,7 +54,11 @@ def test_pointwise_u8_full_range(ictx, mn, oracle_mod, cin, cout, h, n):
 
 
 @pytest.mark.parametrize("c,h,stride,pad,n", [(32, 112, 1, 0, 1), (64, 112, 2, 0, 1), (64, 112, 2, 1, 2), (512, 14, 1, 0, 5),
-                                              (512, 14, 2, 1, 3), (1024, 7, 1, 0, 4), (8, 9, 1, 0, 2)])
+                                              (512, 14, 2, 1, 3), (1024, 7, 1, 0, 4), (8, 9, 1, 0, 2),
+                                              # every tile shape of the shared-memory kernel (>= 128 channels), both paddings
+                                              (128, 56, 1, 0, 1), (128, 56, 1, 1, 2), (128, 56, 2, 0, 1), (256, 28, 1, 1, 1),
+                                              (256, 28, 2, 0, 2), (256, 28, 2, 1, 1), (512, 14, 1, 1, 2), (1024, 7, 1, 1, 3),
+                                              (384, 20, 1, 0, 1), (128, 10, 2, 1, 3)])
 def test_depthwise_u8_full_range(ictx, mn, oracle_mod, c, h, stride, pad, n):
     if h % stride:
         pytest.skip("odd size with stride 2")
