@@ -227,7 +227,6 @@ def integer_mode_throughput(mn, synth, dev_index, batch=256, steps=10):
     for _ in range(3):
         c.forward_device(img.data_ptr(), batch, lg.data_ptr(), t1.data_ptr(), p1.data_ptr())
     c.sync()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -392,7 +391,7 @@ def run_ours(args):
             if use_nccl:
                 g_logits = gathered
             else:
-                lp, tp, pp = ctx.gather_ptrs()
+                lp, _tp, _pp = ctx.gather_ptrs()
                 g_logits = _device_view(torch, lp, (world * batch, 1000), dev)
             own_ok = bool(torch.equal(g_logits[rank * batch:(rank + 1) * batch], logits))
             bits = g_logits.view(torch.int32).to(torch.int64)      # exact, order-independent digests of the block's bits
