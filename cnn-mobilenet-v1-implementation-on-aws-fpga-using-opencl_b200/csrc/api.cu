@@ -37,6 +37,7 @@ const mnv1::Switches& mnv1::switches() {
                                                              // stencil-bound at 67 us per block against 45 us for the two kernels
     sw.pp_direct = getenv("MNV1_PP_DIRECT") != nullptr;
     sw.no_pp_tail = getenv("MNV1_NO_PP_TAIL") != nullptr;
+    sw.h2d_wc = getenv("MNV1_H2D_WC") != nullptr;       // write-combined source buffers in mnv1_h2d_probe_*
     sw.rb_mask = getenv("MNV1_RB_MASK") ? strtol(getenv("MNV1_RB_MASK"), nullptr, 0) : ~0L;
   });
   return sw;
@@ -1535,7 +1536,7 @@ int mnv1_h2d_probe_open(mnv1_ctx* ctx, size_t bytes, mnv1_h2d_probe_t** out) {
   p->ctx = ctx; p->bytes = bytes;
   cudaError_t e = cudaMalloc(&p->d, bytes);
   for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
-    e = cudaHostAlloc(&p->h[i], bytes, getenv("MNV1_H2D_WC") ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    e = cudaHostAlloc(&p->h[i], bytes, mnv1::switches().h2d_wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
     if (e == cudaSuccess) memset(p->h[i], i + 1, bytes);
   }
   if (e == cudaSuccess) e = cudaEventCreate(&p->e0);

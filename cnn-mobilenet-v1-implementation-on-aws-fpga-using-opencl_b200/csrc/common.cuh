@@ -99,7 +99,7 @@ namespace mnv1 {
 bool pdl_enabled();
 // Environment switches (fall back to the previous kernel of a layer; timing experiments): read ONCE per
 // process, by the first mnv1_ctx_create — never from a launch path.
-struct Switches { bool no_pdl, no_pair, no_cw, no_stem_rows, fused_head, fused_pair, pp_direct, no_pp_tail; long rb_mask; };
+struct Switches { bool no_pdl, no_pair, no_cw, no_stem_rows, fused_head, fused_pair, pp_direct, no_pp_tail, h2d_wc; long rb_mask; };
 const Switches& switches();
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remembered per (function,
 // current device), thread-safe, so that a second context on another GPU of the same process opts in too.
