@@ -25,7 +25,7 @@ for line in sass.splitlines():
     if cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
         counts[cur]["instr"] += 1
         for k in KEYS:
-            if k in line:
+            if (" HMMA" in line) if k == "HMMA" else (k in line):     # HMMA (mma.sync) is not UTCHMMA
                 counts[cur][k] += 1
 print(f"# {os.path.basename(lib)}: SASS mnemonics per kernel (tools/sass_mnemonics.py); columns: static instruction counts")
 def short(name):
